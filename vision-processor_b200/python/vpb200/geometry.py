@@ -1,0 +1,229 @@
+"""Host-side geometry: the scalar arguments the detection kernels are launched with.
+
+Dependency-free restatement (numpy, fp32 element ops) of the parts of the reference that turn a
+camera calibration + field size into hot-path inputs:
+
+* ``CameraModel``            src/CameraModel.cpp:63-172 (pinhole + k2 model, field2image/image2field)
+* ``Perspective.geometry_check``  src/Perspective.cpp:35-125 (fieldScale, visible extent, flat size, blob radii)
+* ``Perspective.cl_camera_model`` src/Perspective.cpp:136-150 (the packed 72-byte kernel argument)
+* ``launch_params``          the per-launch scalars of src/Resources.cpp:159-163 and src/main.cpp:289
+
+This runs once per geometry change on the CPU; it is not on the per-frame path.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field as dc_field
+
+import numpy as np
+
+F32 = np.float32
+
+# src/pattern.h:55-56
+CENTER_BLOB_RADIUS = 25.0
+SIDE_BLOB_RADIUS = 20.0
+
+
+@dataclass
+class FieldSize:
+    """The subset of SSL_GeometryFieldSize the path reads (geometry-divA.yml:19-33 defaults)."""
+
+    field_length: float = 12000.0
+    field_width: float = 9000.0
+    boundary_width: float = 300.0
+    boundary_width_goal_line: float | None = 300.0
+    ball_radius: float = 21.5
+    max_robot_radius: float = 90.0
+    line_thickness: float = 10.0
+    center_circle_radius: float = 500.0
+    penalty_area_depth: float = 1800.0
+    penalty_area_width: float = 3600.0
+
+    def goal_boundary_width(self) -> float:  # CameraModel.cpp:20-22
+        return self.boundary_width if self.boundary_width_goal_line is None else self.boundary_width_goal_line
+
+
+def quat_to_matrix(w: float, x: float, y: float, z: float) -> np.ndarray:
+    """Eigen::Quaternionf::toRotationMatrix of the normalised quaternion (row-major 3x3, fp32)."""
+    n = math.sqrt(w * w + x * x + y * y + z * z)
+    w, x, y, z = w / n, x / n, y / n, z / n
+    return np.array(
+        [
+            [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+            [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+            [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)],
+        ],
+        dtype=F32,
+    )
+
+
+@dataclass
+class CameraModel:
+    """src/CameraModel.h:26-58.  Sizes are in QUAD pixels for Bayer cameras (spinnakerdriver.cpp:124)."""
+
+    size: tuple = (1224, 1024)               # CameraModel.cpp:63
+    focal_length: float = 1224.0
+    principal_point: tuple = (612.0, 512.0)
+    distortion_k2: float = 0.0
+    pos: tuple = (0.0, 0.0, 5000.0)          # CameraModel.h:49
+    quat_wxyz: tuple = (0.0, -1.0, 0.0, 0.0)  # CameraModel.h:50
+
+    def f2i(self) -> np.ndarray:
+        return quat_to_matrix(*self.quat_wxyz)
+
+    def ensure_size(self, new_size) -> None:  # CameraModel.cpp:124-135
+        if tuple(self.size) == tuple(new_size):
+            return
+        factor = float(F32(new_size[0]) / F32(self.size[0]))
+        self.size = tuple(new_size)
+        self.focal_length = float(F32(self.focal_length) * F32(factor))
+        self.principal_point = tuple(float(F32(p) * F32(factor)) for p in self.principal_point)
+
+    def field2image(self, p: np.ndarray, iterations: int = 10) -> np.ndarray:
+        """CameraModel.cpp:147-157 (CPU twin: 10 iterations; the kernel uses 8).  p: (...,3) -> (...,2)."""
+        p = np.asarray(p, F32)
+        ray = (p - np.asarray(self.pos, F32)) @ self.f2i().T
+        n = ray[..., :2] / ray[..., 2:3]
+        u = n.copy()
+        k2 = F32(self.distortion_k2)
+        for _ in range(iterations):
+            u = n / (F32(1) + k2 * np.sum(u * u, axis=-1, keepdims=True))
+        return F32(self.focal_length) * u + np.asarray(self.principal_point, F32)
+
+    def image2field(self, p: np.ndarray, height: float) -> np.ndarray:
+        """CameraModel.cpp:137-141,159-172.  p: (...,2) image px -> (...,3) field mm at z=height."""
+        p = np.asarray(p, F32)
+        n = (p - np.asarray(self.principal_point, F32)) / F32(self.focal_length)
+        n = n * (F32(1) + F32(self.distortion_k2) * np.sum(n * n, axis=-1, keepdims=True))
+        ray = np.concatenate([n, np.ones(n.shape[:-1] + (1,), F32)], axis=-1) @ self.f2i()  # i2f = f2i^T
+        pos = np.asarray(self.pos, F32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = ray * ((F32(height) - pos[2]) / ray[..., 2:3]) + pos
+        out[..., 2] = F32(height)
+        out[ray[..., 2] >= 0] = np.nan
+        return out.astype(F32)
+
+
+def pack_cl_camera_model(model: CameraModel) -> bytes:
+    """Perspective::getCLCameraModel, src/Perspective.cpp:136-150 -> 72 packed bytes (Perspective.h:22-29)."""
+    r = model.f2i().reshape(-1)
+    buf = np.zeros(72, np.uint8)
+    buf[0:8] = np.array(model.size, "<i4").view(np.uint8)
+    buf[8:12] = np.array([model.focal_length], "<f4").view(np.uint8)
+    buf[12:20] = np.array(model.principal_point, "<f4").view(np.uint8)
+    buf[20:24] = np.array([model.distortion_k2], "<f4").view(np.uint8)
+    buf[24:60] = r.astype("<f4").view(np.uint8)
+    buf[60:72] = np.array(model.pos, "<f4").view(np.uint8)
+    return buf.tobytes()
+
+
+@dataclass
+class Perspective:
+    """src/Perspective.h:32-58 without the socket: the calibration is handed in directly."""
+
+    model: CameraModel
+    field: FieldSize = dc_field(default_factory=FieldSize)
+    geometry_tolerance: float = 10.0      # Resources.cpp:85
+    visible_field_extent: tuple = (0.0, 0.0, 0.0, 0.0)  # xmin, xmax, ymin, ymax
+    field_scale: float = 5.0
+    reprojected_field_size: tuple = (0, 0)
+    min_blob_radius: float = 20.0
+    max_blob_radius: float = 25.0
+
+    def geometry_check(self, width: int, height: int, max_bot_height: float, resampling_factor: float = 1.0) -> None:
+        """src/Perspective.cpp:35-125 (width/height in quad px for Bayer cameras)."""
+        m, f = self.model, self.field
+        m.ensure_size((width, height))
+        self.min_blob_radius = min(CENTER_BLOB_RADIUS, SIDE_BLOB_RADIUS, f.ball_radius)  # :69
+        self.max_blob_radius = max(CENTER_BLOB_RADIUS, SIDE_BLOB_RADIUS, f.ball_radius)  # :70
+
+        # :72-91 optimal field scale = mean neighbour distance of in-field pixels
+        ys, xs = np.mgrid[0:height, 0:width].astype(F32)
+        pts = m.image2field(np.stack([xs, ys], -1), max_bot_height)[..., :2]
+        pos = pts[:-1, :-1]
+        inside = (np.abs(pos[..., 0]) < F32(f.field_length / 2 + f.goal_boundary_width())) & (
+            np.abs(pos[..., 1]) < F32(f.field_width / 2 + f.boundary_width))
+        dx = np.linalg.norm(pts[:-1, 1:] - pos, axis=-1)
+        dy = np.linalg.norm(pts[1:, :-1] - pos, axis=-1)
+        n = 2 * int(inside.sum())
+        s = float((dx[inside].astype(np.float64) + dy[inside].astype(np.float64)).sum())
+        self.field_scale = float(F32(F32(s / n) * F32(resampling_factor)))
+
+        # :94-105 visible extent from the image border
+        border = np.concatenate([
+            np.stack([np.arange(width, dtype=F32), np.zeros(width, F32)], -1),
+            np.stack([np.arange(width, dtype=F32), np.full(width, height - 1, F32)], -1),
+            np.stack([np.zeros(height, F32), np.arange(height, dtype=F32)], -1),
+            np.stack([np.full(height, width - 1, F32), np.arange(height, dtype=F32)], -1),
+        ])
+        bp = m.image2field(border, max_bot_height)[..., :2]
+        ext = [np.nanmin(bp[:, 0]), np.nanmax(bp[:, 0]), np.nanmin(bp[:, 1]), np.nanmax(bp[:, 1])]
+        # :107-113 clamp to the field
+        half_l = F32(f.field_length / 2 + f.goal_boundary_width() + self.geometry_tolerance)
+        half_w = F32(f.field_width / 2 + f.boundary_width + self.geometry_tolerance)
+        ext = [max(ext[0], -half_l), min(ext[1], half_l), max(ext[2], -half_w), min(ext[3], half_w)]
+        self.visible_field_extent = tuple(float(F32(e)) for e in ext)
+
+        # :115-122 flat size, rounded to nearest, forced even
+        fs = F32(self.field_scale)
+        w = int(np.rint(F32(F32(ext[1]) - F32(ext[0])) / fs))
+        h = int(np.rint(F32(F32(ext[3]) - F32(ext[2])) / fs))
+        self.reprojected_field_size = (w + (w % 2), h + (h % 2))
+
+    def flat2field(self, pos):  # :127-129
+        return np.asarray(pos, F32) * F32(self.field_scale) + np.array(
+            [self.visible_field_extent[0], self.visible_field_extent[2]], F32)
+
+    def field2flat(self, pos):  # :131-133
+        return (np.asarray(pos, F32) - np.array(
+            [self.visible_field_extent[0], self.visible_field_extent[2]], F32)) / F32(self.field_scale)
+
+
+@dataclass
+class LaunchParams:
+    """Every scalar the seven live kernels receive for one camera geometry."""
+
+    fmt: int
+    wq: int
+    hq: int
+    wf: int
+    hf: int
+    model_bytes: bytes            # 72-byte CLCameraModel
+    max_robot_height: float       # (float)gcSocket->maxBotHeight          Resources.cpp:159
+    field_scale: float            # perspective->fieldScale                Resources.cpp:159
+    off_x: float                  # visibleFieldExtent[0]                  Resources.cpp:159
+    off_y: float                  # visibleFieldExtent[2]                  Resources.cpp:159
+    grad_offset: int              # (int)ceilf(maxBlobRadius/scale) / 3    Resources.cpp:160
+    circle_radius: int            # (int)ceilf(minBlobRadius/scale)        Resources.cpp:163
+    circ_threshold: float = 15.0  # thresholds.circularity                 Resources.cpp:190
+    min_score: float = 0.0        # literal at the call site               main.cpp:289
+    blob_radius: int = 0          # (int)floorf(minBlobRadius/scale)       main.cpp:289
+    max_blobs: int = 2000         # thresholds.blobs                       Resources.cpp:84
+    sample_mode: int = 0
+
+
+def launch_params(persp: Perspective, fmt: int, wq: int, hq: int, max_bot_height: float = 180.0,
+                  circ_threshold: float = 15.0, max_blobs: int = 2000, sample_mode: int = 0) -> LaunchParams:
+    s = F32(persp.field_scale)
+    wf, hf = persp.reprojected_field_size
+    return LaunchParams(
+        fmt=fmt, wq=wq, hq=hq, wf=wf, hf=hf,
+        model_bytes=pack_cl_camera_model(persp.model),
+        max_robot_height=float(F32(max_bot_height)),
+        field_scale=float(s),
+        off_x=float(F32(persp.visible_field_extent[0])),
+        off_y=float(F32(persp.visible_field_extent[2])),
+        grad_offset=int(math.ceil(float(F32(persp.max_blob_radius) / s))) // 3,
+        circle_radius=int(math.ceil(float(F32(persp.min_blob_radius) / s))),
+        circ_threshold=circ_threshold,
+        min_score=0.0,
+        blob_radius=int(math.floor(float(F32(persp.min_blob_radius) / s))),
+        max_blobs=max_blobs,
+        sample_mode=sample_mode,
+    )
+
+
+def default_camera(wq: int, hq: int, k2: float = 0.0, height: float = 5000.0) -> CameraModel:
+    """SURVEY section 8(d) synthetic camera: top-down pinhole, f = Wq quad px, centred principal point."""
+    return CameraModel(size=(wq, hq), focal_length=float(wq), principal_point=(wq / 2.0, hq / 2.0),
+                       distortion_k2=k2, pos=(0.0, 0.0, height), quat_wxyz=(0.0, -1.0, 0.0, 0.0))
