@@ -1,0 +1,223 @@
+/*
+ * vp_b200.h -- C ABI of libvp_b200.so, the B200-native (sm_100a CUDA) replacement for the
+ * OpenCL layer of TIGERs-Mannheim/vision-processor (src/opencl.h, src/opencl.cpp) and the
+ * 13 kernels under kernel/ *.cl.
+ *
+ * All citations are path:line in the reference tree.  Every entry point returns a vp_status
+ * (0 = ok) unless noted; the text of the last failure is available through vp_last_error().
+ * The reference turns every OpenCL failure into FATAL = log + exit(1) (src/log.h:21,
+ * src/opencl.h:81-83); the C++ shim include/compat/opencl.h restores that behaviour on top
+ * of these status codes.
+ *
+ * Threading: kernels are launched from ONE thread per context (the reference launches only
+ * from its main thread, src/main.cpp:262-423); buffers and images may be mapped and unmapped
+ * from other threads (src/rtpstreamer.cpp:177, src/snapshotwriter.cpp:52-54).
+ *
+ * There is no CPU fallback: without a CUDA device vp_ctx_create fails.
+ */
+#ifndef VP_B200_H
+#define VP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VP_API __attribute__((visibility("default")))
+#else
+#define VP_API
+#endif
+
+typedef enum {
+	VP_OK = 0,
+	VP_ERR_INVALID = 1,     /* bad argument (null handle, size mismatch, unknown format) */
+	VP_ERR_CUDA = 2,        /* a CUDA runtime call failed; see vp_last_error */
+	VP_ERR_NOMEM = 3,
+	VP_ERR_UNSUPPORTED = 4,
+	VP_ERR_NO_DEVICE = 5
+} vp_status;
+
+/* PixelFormat table, src/opencl.cpp:24-31 / src/opencl.h:30-56.  pixelSize = stride*rowStride. */
+typedef enum {
+	VP_FMT_RGGB8 = 0, /* stride 2, rowStride 2, "-DRGGB"; width/height count QUADS (spinnakerdriver.cpp:124) */
+	VP_FMT_GRBG8 = 1, /* stride 2, rowStride 2, "-DGRBG" */
+	VP_FMT_BGR8 = 2,  /* stride 3, rowStride 1, "-DBGR" */
+	VP_FMT_RGBA8 = 3, /* stride 4 */
+	VP_FMT_U8 = 4,    /* stride 1 */
+	VP_FMT_F32 = 5,   /* stride 4 */
+	VP_FMT_NV12 = 6   /* stride 1, rowStride 2 (allocated 2*w*h, 1.5*w*h used; opencl.cpp:27) */
+} vp_format;
+
+VP_API int vp_format_pixel_size(int fmt); /* PixelFormat::pixelSize(), opencl.h:44 */
+
+/* What read_imageui + CLK_FILTER_LINEAR means on an integer image (left to the OpenCL runtime:
+ * resampling.cl:50, quad2nv12.cl:21, quad2rgba.cl:21).  Default = bilinear per the OpenCL 1.2
+ * formula in fp32 (no FMA), converted round-to-nearest-even. */
+typedef enum { VP_SAMPLE_BILINEAR_RTE = 0, VP_SAMPLE_BILINEAR_TRUNC = 1, VP_SAMPLE_NEAREST = 2 } vp_sample_mode;
+
+/* CLCameraModel: src/Perspective.h:22-29 == kernel/resampling.cl:20-27, packed, 72 bytes, by value */
+typedef struct __attribute__((packed)) {
+	int32_t shape[2];
+	float f;     /* focal length in (quad) px */
+	float p[2];  /* principal point */
+	float d;     /* k2 distortion */
+	float r[9];  /* row-major field->image rotation */
+	float c[3];  /* camera position, mm */
+} vp_camera_model;
+
+/* CLMatch: src/main.cpp:33-41 == kernel/blobList.cl:20-32, packed, 22 bytes */
+typedef struct __attribute__((packed)) {
+	float x, y;
+	uint8_t color[3];
+	uint8_t center[3];
+	float circ;
+	float score;
+} vp_match;
+
+/* Every scalar the seven live kernels receive for one camera geometry
+ * (src/Resources.cpp:159-163, src/main.cpp:289). */
+typedef struct {
+	int32_t fmt;  /* VP_FMT_RGGB8 | VP_FMT_GRBG8 | VP_FMT_BGR8 */
+	int32_t wq, hq; /* RawImage width/height: quads for Bayer, pixels for BGR */
+	int32_t wf, hf; /* Perspective::reprojectedFieldSize (even, Perspective.cpp:115-122) */
+	vp_camera_model model;
+	float max_robot_height; /* (float)gcSocket->maxBotHeight */
+	float field_scale;
+	float off_x, off_y;     /* visibleFieldExtent[0], [2] */
+	int32_t grad_offset;    /* (int)ceilf(maxBlobRadius/fieldScale) / 3 */
+	int32_t circle_radius;  /* (int)ceilf(minBlobRadius/fieldScale) */
+	float circ_threshold;   /* thresholds.circularity */
+	float min_score;        /* literal 0.0f at main.cpp:289 */
+	int32_t blob_radius;    /* (int)floorf(minBlobRadius/fieldScale) */
+	int32_t max_blobs;      /* thresholds.blobs */
+	int32_t sample_mode;    /* vp_sample_mode */
+} vp_params;
+
+typedef struct vp_ctx vp_ctx;   /* class OpenCL, opencl.h:69-112: device + in-order queue + pools */
+typedef struct vp_buf vp_buf;   /* class CLArray / RawImage storage, opencl.h:154-188 */
+typedef struct vp_img vp_img;   /* class CLImage storage, opencl.h:195-212 */
+
+/* ---- context (OpenCL::OpenCL, opencl.cpp:34-50) ------------------------------------------- */
+VP_API int vp_ctx_create(int device_ordinal, vp_ctx** out);
+VP_API void vp_ctx_destroy(vp_ctx* ctx);
+VP_API const char* vp_last_error(const vp_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+VP_API int vp_ctx_sync(vp_ctx* ctx);                  /* OpenCL::wait on everything enqueued so far */
+VP_API void* vp_ctx_stream(vp_ctx* ctx);              /* the cudaStream_t all stages are launched on */
+VP_API int vp_device_count(void);
+
+/* per-launch profiling, OpenCL::run/printRuntimes/clearEvents (opencl.h:76-96, opencl.cpp:94-105).
+ * Disabled by default; when enabled every stage call records a CUDA event pair. */
+VP_API int vp_profiling_enable(vp_ctx* ctx, int on);
+VP_API int vp_profiling_count(vp_ctx* ctx);
+VP_API int vp_profiling_get(vp_ctx* ctx, int i, const char** stage_name, float* ms); /* blocks on the event */
+VP_API int vp_profiling_clear(vp_ctx* ctx);
+
+/* ---- buffers (CLArray, opencl.cpp:146-147) -------------------------------------------------
+ * Device memory with a pinned host mirror.  map(READ) copies device->host and blocks;
+ * unmap after map(WRITE|READWRITE) copies host->device and blocks (opencl.h:115-152).
+ * Read maps hand out writable memory (blob_benchmark.cpp:190-191 sorts a read map in place). */
+enum { VP_MAP_READ = 1, VP_MAP_WRITE = 2 /* invalidate */, VP_MAP_READWRITE = 3 };
+VP_API int vp_buf_alloc(vp_ctx* ctx, size_t bytes, vp_buf** out);                        /* CL_MEM_ALLOC_HOST_PTR */
+VP_API int vp_buf_alloc_copy(vp_ctx* ctx, const void* host, size_t bytes, vp_buf** out); /* CL_MEM_COPY_HOST_PTR */
+VP_API int vp_buf_retain(vp_buf* buf);  /* RawImage copies share the buffer (opencl.h:170) */
+VP_API int vp_buf_release(vp_buf* buf);
+VP_API int vp_buf_map(vp_buf* buf, int mode, void** host);
+VP_API int vp_buf_unmap(vp_buf* buf);
+VP_API size_t vp_buf_size(const vp_buf* buf);
+VP_API void* vp_buf_device_ptr(vp_buf* buf);
+
+/* ---- images (CLImage, opencl.cpp:149-158); formats RGBA8, U8, F32; dense pitch -------------- */
+VP_API int vp_img_alloc(vp_ctx* ctx, int fmt, int width, int height, vp_img** out);
+VP_API int vp_img_retain(vp_img* img);
+VP_API int vp_img_release(vp_img* img);
+VP_API int vp_img_map(vp_img* img, int mode, void** host, size_t* byte_pitch); /* CLImageMap, opencl.h:215-262 */
+VP_API int vp_img_unmap(vp_img* img);
+VP_API int vp_img_info(const vp_img* img, int* fmt, int* width, int* height);
+VP_API void* vp_img_device_ptr(vp_img* img);
+
+/* ---- stages: one call per reference kernel, asynchronous on the context stream -------------- */
+/* kernel/raw2quad.cl:21-39, launch Resources.cpp:138-143 (NDRange wq x hq) */
+VP_API int vp_raw2quad(vp_ctx* ctx, const vp_buf* raw, int fmt, int wq, int hq, vp_img* const ch[4]);
+/* kernel/resampling.cl:52-99, launch Resources.cpp:159 (NDRange = size of `flat`) */
+VP_API int vp_resampling(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* flat, const vp_camera_model* model,
+                         float max_robot_height, float field_scale, float off_x, float off_y, int sample_mode);
+/* kernel/gradientDot.cl:22-30, launch Resources.cpp:160 */
+VP_API int vp_gradient_dot(vp_ctx* ctx, const vp_img* rgba, vp_img* out, int offset);
+/* kernel/satHorizontal.cl:22-31 (NDRange height), kernel/satVertical.cl:22-31 (NDRange width); Resources.cpp:161-162 */
+VP_API int vp_sat_horizontal(vp_ctx* ctx, const vp_img* in, vp_img* out);
+VP_API int vp_sat_vertical(vp_ctx* ctx, const vp_img* in, vp_img* out);
+/* kernel/satBlobCenter.cl:22-42, launch Resources.cpp:163 */
+VP_API int vp_circle(vp_ctx* ctx, const vp_img* sat, vp_img* out, int radius);
+/* kernel/blobList.cl:36-102, launch main.cpp:289.  matches: >= 22*max_matches bytes; counter: 3 x int32,
+ * incremented from the values it holds (the caller zeroes it, main.cpp:283-288).  Blobs are emitted in raster
+ * order (y-major); on overflow the first max_matches in that order are kept and counter[0] keeps counting. */
+VP_API int vp_blob_list(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_buf* matches, vp_buf* counter,
+                        float circ_threshold, float min_score, int radius, int max_matches);
+/* kernel/rgba2nv12.cl:22-31, f2nv12.cl:22-26 (Resources.cpp:172-186); quad2nv12.cl:23-58 (Resources.cpp:166-170);
+ * quad2rgba.cl:23-53 (Resources.cpp:145-149).  The racing UV writes of the reference are resolved to the
+ * bottom-right pixel of each 2x2 block (the last writer of a sequential raster-order run). */
+VP_API int vp_rgba2nv12(vp_ctx* ctx, const vp_img* rgba, vp_buf* nv12);
+VP_API int vp_f2nv12(vp_ctx* ctx, const vp_img* f32, vp_buf* nv12);
+VP_API int vp_quad2nv12(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_buf* nv12, int sample_mode);
+VP_API int vp_quad2rgba(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* rgba, int sample_mode);
+/* dead kernels named by north_star: kernel/blobCenter.cl:29-63 (never compiled), kernel/blobScore.cl:23-66
+ * (enqueue commented out, blob_benchmark.cpp:154-155) */
+VP_API int vp_circularize(vp_ctx* ctx, const vp_img* in, vp_img* out, int min_blob_radius, int max_blob_radius);
+VP_API int vp_blob_score(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_img* out, float circ_threshold, int radius);
+
+/* ---- fused detection: Resources::raw2quad + rgba2blobCenter (Resources.cpp:138-164) + counter reset and
+ * blobList (main.cpp:283-289) for `n_frames` frames of one camera geometry, no quad planes materialised.
+ *
+ * Device-pointer form (used by the batch benchmark and by torch/CUDA callers): all pointers are device
+ * memory, frame i at base + i*stride:
+ *   d_raw      n_frames x raw_bytes          (raw_bytes = wq*hq*pixelSize(fmt))
+ *   d_flat     n_frames x wf*hf*4  RGBA8     (dRGB image `flat`)
+ *   d_grad     n_frames x wf*hf    F32       (`gradDot`)
+ *   d_circ     n_frames x wf*hf    F32       (`blobCenter`)
+ *   d_matches  n_frames x max_blobs*22 bytes
+ *   d_counter  n_frames x 3 int32            (zeroed by the call)
+ * Asynchronous on the context stream. */
+VP_API int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* params,
+                                  uint8_t* d_flat, float* d_grad, float* d_circ,
+                                  vp_match* d_matches, int32_t* d_counter);
+
+/* Host form: raw frames in host memory (pinned for full speed, see vp_host_alloc), blob lists and counters
+ * back in host memory; images stay on the device (vp_detect_images).  Blocking.  Internally a ring of
+ * device slots so the upload of frame i+1 overlaps the kernels of frame i. */
+VP_API int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_params* params,
+                          vp_match* h_matches, int32_t* h_counter);
+/* device pointers of the images produced for the LAST frame of the most recent vp_detect_host call */
+VP_API int vp_detect_images(vp_ctx* ctx, const uint8_t** d_flat, const float** d_grad, const float** d_circ);
+/* number of frames of the last fused call whose SAT left the exact-integer range of fp32 (2^24) and were
+ * recomputed in the reference's sequential summation order */
+VP_API int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n);
+
+/* debug-stream conversions straight from a raw frame / detection images (device pointers), Resources.cpp:166-186 */
+VP_API int vp_raw2nv12_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_nv12, int sample_mode);
+VP_API int vp_raw2rgba_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_rgba, int sample_mode);
+VP_API int vp_rgba2nv12_device(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_t* d_nv12);
+VP_API int vp_f2nv12_device(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_nv12);
+
+/* blocking copies ordered after everything enqueued on the context stream (tests, tools) */
+VP_API int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes);
+VP_API int vp_copy_to_device(vp_ctx* ctx, void* dev, const void* host, size_t bytes);
+
+/* pinned host memory for frame sources (the camera drivers' user buffers, spinnakerdriver.cpp:120-133) */
+VP_API int vp_host_alloc(size_t bytes, void** out);
+VP_API int vp_host_free(void* p);
+
+/* tuning knob: frames per kernel launch group of the fused path (0 = automatic: the group's working set is kept
+ * inside the 126 MB L2) */
+VP_API int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group);
+
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+VP_API uint64_t vp_launch_count(const vp_ctx* ctx);
+VP_API const char* vp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VP_B200_H */

@@ -1,0 +1,117 @@
+"""GPU parity of the fused detection path (vp_detect_host / vp_detect_batch_device) against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+import oracle as O
+from vpb200 import lib
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    dict(wq=96, hq=64, fmt=0),
+    dict(wq=102, hq=66, fmt=0, k2=0.12, tilt=0.2),
+    dict(wq=96, hq=64, fmt=1, k2=-0.08, tilt=-0.1, sample_mode=1),
+    dict(wq=128, hq=96, fmt=2, k2=0.05, sample_mode=2),
+    dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7),
+    dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, thr=15.0),
+]
+
+
+def check_frame(got, i, want):
+    np.testing.assert_array_equal(got["counter"][i], want["counter"])
+    common.assert_matches_equal(got["matches"][i], want["matches"])
+
+
+@pytest.mark.parametrize("kw", CASES)
+def test_detect_single_frame(ctx, port, kw):
+    p, raw, _ = common.make_case(**kw)
+    want = port.detect(raw, p)
+    got = ctx.detect(raw, common.to_vp(p))
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+    assert want["max_abs_sat"] < 2 ** 24 and got["sat_fallbacks"] == 0
+
+
+def test_detect_batch_of_distinct_frames(ctx, port):
+    """11 frames (not a multiple of the upload chunk or the launch group), each with its own noise seed."""
+    frames, wants = [], []
+    for s in range(11):
+        p, raw, _ = common.make_case(wq=128, hq=80, seed=s, n_robots=2, n_balls=2)
+        frames.append(raw)
+        wants.append(port.detect(raw, p, want_images=False))
+    got = ctx.detect(np.stack(frames), common.to_vp(p), want_images=False)
+    for i, w in enumerate(wants):
+        check_frame(got, i, w)
+
+
+def test_detect_blob_overflow_keeps_first_in_raster_order(ctx, port):
+    p, raw, _ = common.make_case(wq=160, hq=120, frame="noise", seed=9, max_blobs=50)
+    want = port.detect(raw, p)
+    got = ctx.detect(raw, common.to_vp(p))
+    assert want["counter"][0] > 50 and len(want["matches"]) == 50
+    check_frame(got, 0, want)
+
+
+def test_sat_beyond_2p24_falls_back_to_sequential_order(ctx, port):
+    """A frame whose SAT leaves the exact-integer range of fp32: the reference's sequential rounding is reproduced."""
+    p, _, _ = common.make_case(wq=256, hq=256, scale_mm=4.0)
+    # vertical bars shifted by one row per column -> gx*gy has one sign everywhere -> |SAT| grows monotonically
+    h, w = 2 * p.hq, 2 * p.wq
+    yy, xx = np.mgrid[0:h, 0:w]
+    raw = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
+    want = port.detect(raw, p)
+    assert want["max_abs_sat"] > 2 ** 24
+    got = ctx.detect(raw, common.to_vp(p))
+    assert got["sat_fallbacks"] == 1
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+
+
+def test_detect_device_pointer_api_matches_host_api(ctx, port):
+    p, raw, _ = common.make_case(wq=128, hq=96, n_robots=2, seed=4)
+    vp = common.to_vp(p)
+    n, nf, rb = 5, p.wf * p.hf, raw.size
+    raws = np.stack([np.roll(raw, 2 * 2 * p.wq * k) for k in range(n)])  # shift by whole quad rows
+    host = ctx.detect(raws, vp, want_images=False)
+    bufs = dict(raw=ctx.buffer(n * rb, raws), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
+    for group in (1, 2, 0):
+        ctx.set_group(group)
+        ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                                bufs["m"].device_ptr, bufs["c"].device_ptr)
+        counter = bufs["c"].read(np.int32).reshape(n, 3)
+        m = bufs["m"].read(np.uint8).reshape(n, vp.max_blobs, 22)
+        np.testing.assert_array_equal(counter, host["counter"])
+        for i in range(n):
+            k = int(counter[i, 0])
+            np.testing.assert_array_equal(m[i, :k], common.match_bytes(host["matches"][i]))
+    for i in range(n):
+        check_frame(host, i, port.detect(raws[i], p, want_images=False))
+    for b in bufs.values():
+        b.release()
+
+
+def test_full_size_headline_config(ctx, port):
+    """BASELINE config 2: one 2448x2048 BayerRG8 frame, full detection, bit-exact against the oracle."""
+    from vpb200 import geometry as G, synth as S
+    wq, hq = 1224, 1024
+    cam = G.default_camera(wq, hq, k2=0.0)
+    persp = G.Perspective(cam)
+    persp.geometry_check(wq, hq, 180.0)
+    lp = G.launch_params(persp, 0, wq, hq)
+    scene = S.random_scene(persp.visible_field_extent, 16, 4, seed=1)
+    raw = S.render_raw(scene, cam, 2 * wq, 2 * hq, seed=1).reshape(-1)
+    p = common.to_vpo(lp)
+    want = port.detect(raw, p)
+    got = ctx.detect(raw, common.to_vp(p))
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+    assert len(want["matches"]) >= 16 * 5  # every pattern blob is a peak

@@ -1,0 +1,1155 @@
+/*
+ * vp_b200.cu -- host side of libvp_b200.so: the C ABI declared in include/vp_b200.h.
+ *
+ * Replaces src/opencl.cpp of the reference (context, in-order queue, host-mappable buffers and
+ * images, kernel launches) and the launch sequences of src/Resources.cpp:138-186 and
+ * src/main.cpp:283-289.  Plain CUDA runtime; no torch types, no CPU fallback.
+ */
+#include "kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace vpk;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+struct LutEntry {
+	uint8_t key[96];
+	float2* d = nullptr;
+	uint64_t stamp = 0;
+};
+
+struct ProfEntry {
+	const char* name;
+	cudaEvent_t start, stop;
+};
+
+constexpr int HOST_SLOTS = 3;
+
+struct HostSlot {
+	uint8_t* raw = nullptr;
+	uint8_t* flat = nullptr;
+	float* grad = nullptr;
+	float* circ = nullptr;
+	vp_match* matches = nullptr;
+	int32_t* counter = nullptr;
+	cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+};
+
+} // namespace
+
+struct vp_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+	std::mutex mu;
+	std::string err;
+	std::atomic<uint64_t> launches{ 0 };
+	bool profiling = false;
+	std::vector<ProfEntry> prof;
+
+	std::vector<LutEntry> luts;
+	uint64_t lut_clock = 0;
+
+	/* scratch of the fused path, sized for `group` frames of nf pixels / hf rows */
+	int32_t* rowsum = nullptr;
+	float* sat = nullptr;
+	size_t scratch_px = 0;
+	int32_t* rowcount = nullptr;
+	int32_t* first_slot = nullptr;
+	int* flag = nullptr;
+	size_t rows_cap = 0, frames_cap = 0;
+	int group = 0; /* 0 = choose from the frame size */
+	int last_fallbacks = 0;
+	int* flag_host = nullptr; /* pinned */
+
+	HostSlot slots[HOST_SLOTS];
+	size_t slot_frames = 0, slot_raw = 0, slot_nf = 0, slot_blobs = 0;
+	const uint8_t* last_flat = nullptr;
+	const float* last_grad = nullptr;
+	const float* last_circ = nullptr;
+};
+
+struct vp_buf {
+	vp_ctx* ctx;
+	void* d = nullptr;
+	void* h = nullptr;
+	size_t size = 0;
+	std::atomic<int> refs{ 1 };
+	int mapped = 0;
+	std::mutex mu;
+};
+
+struct vp_img {
+	vp_ctx* ctx;
+	int fmt, w, h;
+	vp_buf* buf;
+	std::atomic<int> refs{ 1 };
+};
+
+namespace {
+
+int fail(vp_ctx* ctx, int code, const char* fmt, ...)
+{
+	char msg[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(msg, sizeof msg, fmt, ap);
+	va_end(ap);
+	t_last_error = msg;
+	if (ctx) {
+		std::lock_guard<std::mutex> l(ctx->mu);
+		ctx->err = msg;
+	}
+	return code;
+}
+
+#define CK(ctx, call)                                                                                                  \
+	do {                                                                                                               \
+		cudaError_t e_ = (call);                                                                                       \
+		if (e_ != cudaSuccess)                                                                                         \
+			return fail(ctx, e_ == cudaErrorMemoryAllocation ? VP_ERR_NOMEM : VP_ERR_CUDA, "%s: %s (%s:%d)", #call,   \
+			            cudaGetErrorString(e_), __FILE__, __LINE__);                                                   \
+	} while (0)
+
+#define REQUIRE(ctx, cond, ...)                                                                                        \
+	do {                                                                                                               \
+		if (!(cond))                                                                                                   \
+			return fail(ctx, VP_ERR_INVALID, __VA_ARGS__);                                                             \
+	} while (0)
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+/* RAII-less stage scope: counts the launch and, when profiling, brackets it with events */
+struct Stage {
+	vp_ctx* c;
+	int idx = -1;
+	Stage(vp_ctx* ctx, const char* name, int n_launches = 1): c(ctx)
+	{
+		c->launches += (uint64_t)n_launches;
+		if (c->profiling) {
+			if (c->prof.size() >= 4096) /* blob_benchmark never clears its events (blob_benchmark.cpp); keep it bounded */
+				return;
+			ProfEntry e{ name, nullptr, nullptr };
+			cudaEventCreate(&e.start);
+			cudaEventCreate(&e.stop);
+			cudaEventRecord(e.start, c->stream);
+			c->prof.push_back(e);
+			idx = (int)c->prof.size() - 1;
+		}
+	}
+	~Stage()
+	{
+		if (idx >= 0)
+			cudaEventRecord(c->prof[idx].stop, c->stream);
+	}
+};
+
+int check_launch(vp_ctx* ctx, const char* what)
+{
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess)
+		return fail(ctx, VP_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+	return VP_OK;
+}
+
+bool is_raw_fmt(int fmt) { return fmt == VP_FMT_RGGB8 || fmt == VP_FMT_GRBG8 || fmt == VP_FMT_BGR8; }
+bool is_mode(int m) { return m == VP_SAMPLE_BILINEAR_RTE || m == VP_SAMPLE_BILINEAR_TRUNC || m == VP_SAMPLE_NEAREST; }
+
+/* ---- template dispatch over (format, sample mode) ------------------------------------------ */
+#define VP_DISPATCH_MODE(FMT, mode, CALL)                                                                              \
+	switch (mode) {                                                                                                    \
+	case VP_SAMPLE_BILINEAR_RTE: { constexpr int MODE = MODE_RTE; constexpr int FMTC = FMT; CALL; } break;             \
+	case VP_SAMPLE_BILINEAR_TRUNC: { constexpr int MODE = MODE_TRUNC; constexpr int FMTC = FMT; CALL; } break;         \
+	default: { constexpr int MODE = MODE_NEAREST; constexpr int FMTC = FMT; CALL; } break;                             \
+	}
+
+/* coordinate table of a geometry, cached per context (a handful of geometries at most: one per camera) */
+int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, float offx, float offy, int wf, int hf, const float2** out)
+{
+	uint8_t key[96];
+	memset(key, 0, sizeof key);
+	memcpy(key, m, 72);
+	memcpy(key + 72, &height, 4);
+	memcpy(key + 76, &scale, 4);
+	memcpy(key + 80, &offx, 4);
+	memcpy(key + 84, &offy, 4);
+	memcpy(key + 88, &wf, 4);
+	memcpy(key + 92, &hf, 4);
+	for (LutEntry& e : ctx->luts)
+		if (memcmp(e.key, key, sizeof key) == 0) {
+			e.stamp = ++ctx->lut_clock;
+			*out = e.d;
+			return VP_OK;
+		}
+	LutEntry* slot = nullptr;
+	if (ctx->luts.size() < 8) {
+		ctx->luts.emplace_back();
+		slot = &ctx->luts.back();
+	} else {
+		slot = &ctx->luts[0];
+		for (LutEntry& e : ctx->luts)
+			if (e.stamp < slot->stamp)
+				slot = &e;
+		/* the evicted table may still be read by kernels in flight */
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		CK(ctx, cudaFree(slot->d));
+		slot->d = nullptr;
+	}
+	memcpy(slot->key, key, sizeof key);
+	slot->stamp = ++ctx->lut_clock;
+	cudaError_t e = cudaMalloc(&slot->d, sizeof(float2) * (size_t)wf * hf);
+	if (e != cudaSuccess) {
+		memset(slot->key, 0xff, sizeof slot->key);
+		slot->d = nullptr;
+		return fail(ctx, VP_ERR_NOMEM, "coordinate table allocation failed: %s", cudaGetErrorString(e));
+	}
+	{
+		Stage st(ctx, "coord_table");
+		dim3 b(32, 8), g(cdiv(wf, 32), cdiv(hf, 8));
+		k_coord_table<<<g, b, 0, ctx->stream>>>(slot->d, *m, height, scale, offx, offy, wf, hf);
+	}
+	*out = slot->d;
+	return check_launch(ctx, "k_coord_table");
+}
+
+template <class Src>
+int launch_reproject(vp_ctx* ctx, const Src& src, size_t frame_stride, int fmt, int mode, const float2* lut, uint32_t* flat, int wq,
+                     int hq, int nf, int n_frames)
+{
+	const dim3 g(cdiv(nf, 256), n_frames);
+#define VP_CALL k_reproject<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, frame_stride, lut, flat, wq, hq, nf)
+	if (fmt == VP_FMT_RGGB8) { VP_DISPATCH_MODE(FMT_RGGB, mode, VP_CALL) }
+	else if (fmt == VP_FMT_GRBG8) { VP_DISPATCH_MODE(FMT_GRBG, mode, VP_CALL) }
+	else { VP_DISPATCH_MODE(FMT_BGR, mode, VP_CALL) }
+#undef VP_CALL
+	return check_launch(ctx, "k_reproject");
+}
+
+template <class Src>
+int launch_quad2nv12(vp_ctx* ctx, const Src& src, int fmt, int mode, uint8_t* out, int wq, int hq)
+{
+	const dim3 g(cdiv(wq / 2, 256), hq / 2);
+#define VP_CALL k_quad2nv12<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, out, wq, hq)
+	if (fmt == VP_FMT_RGGB8) { VP_DISPATCH_MODE(FMT_RGGB, mode, VP_CALL) }
+	else if (fmt == VP_FMT_GRBG8) { VP_DISPATCH_MODE(FMT_GRBG, mode, VP_CALL) }
+	else { VP_DISPATCH_MODE(FMT_BGR, mode, VP_CALL) }
+#undef VP_CALL
+	return check_launch(ctx, "k_quad2nv12");
+}
+
+template <class Src>
+int launch_quad2rgba(vp_ctx* ctx, const Src& src, int fmt, int mode, uint32_t* out, int wq, int hq)
+{
+	const dim3 g(cdiv(wq, 256), hq);
+#define VP_CALL k_quad2rgba<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, out, wq, hq)
+	if (fmt == VP_FMT_RGGB8) { VP_DISPATCH_MODE(FMT_RGGB, mode, VP_CALL) }
+	else if (fmt == VP_FMT_GRBG8) { VP_DISPATCH_MODE(FMT_GRBG, mode, VP_CALL) }
+	else { VP_DISPATCH_MODE(FMT_BGR, mode, VP_CALL) }
+#undef VP_CALL
+	return check_launch(ctx, "k_quad2rgba");
+}
+
+int launch_colscan(vp_ctx* ctx, const int32_t* rowsum, float* sat, int wf, int hf, int n_frames, int* flag)
+{
+	const int rpw = cdiv(hf, 32);
+	const dim3 g(cdiv(wf, 32), n_frames);
+	if (rpw <= 16)
+		k_colscan<16><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+	else if (rpw <= 32)
+		k_colscan<32><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+	else if (rpw <= 48)
+		k_colscan<48><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+	else
+		return fail(ctx, VP_ERR_UNSUPPORTED, "flat image height %d exceeds 1536 rows", hf);
+	return check_launch(ctx, "k_colscan");
+}
+
+/* blobList.cl:79 can only reject when minScore > 0 or circularities may be negative */
+int need_score(float thr, float min_score) { return !(min_score <= 0.0f && thr >= 0.0f); }
+
+int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames)
+{
+	if (group_px > ctx->scratch_px) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->rowsum);
+		cudaFree(ctx->sat);
+		ctx->rowsum = nullptr;
+		ctx->sat = nullptr;
+		ctx->scratch_px = 0;
+		CK(ctx, cudaMalloc(&ctx->rowsum, group_px * 4));
+		CK(ctx, cudaMalloc(&ctx->sat, group_px * 4));
+		ctx->scratch_px = group_px;
+	}
+	if (rows > ctx->rows_cap || frames > ctx->frames_cap) {
+		const size_t r = rows > ctx->rows_cap ? rows : ctx->rows_cap, f = frames > ctx->frames_cap ? frames : ctx->frames_cap;
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->rowcount);
+		cudaFree(ctx->first_slot);
+		cudaFree(ctx->flag);
+		if (ctx->flag_host)
+			cudaFreeHost(ctx->flag_host);
+		ctx->rowcount = ctx->first_slot = nullptr;
+		ctx->flag = nullptr;
+		ctx->flag_host = nullptr;
+		ctx->rows_cap = ctx->frames_cap = 0;
+		CK(ctx, cudaMalloc(&ctx->rowcount, r * 4));
+		CK(ctx, cudaMalloc(&ctx->first_slot, f * 4));
+		CK(ctx, cudaMalloc(&ctx->flag, f * 4));
+		CK(ctx, cudaMallocHost(&ctx->flag_host, f * 4));
+		ctx->rows_cap = r;
+		ctx->frames_cap = f;
+	}
+	return VP_OK;
+}
+
+int validate_params(vp_ctx* ctx, const vp_params* p)
+{
+	REQUIRE(ctx, p, "params is null");
+	REQUIRE(ctx, is_raw_fmt(p->fmt), "params.fmt %d is not a raw format", p->fmt);
+	REQUIRE(ctx, p->wq > 0 && p->hq > 0 && p->wf > 0 && p->hf > 0, "non-positive image size");
+	REQUIRE(ctx, (size_t)p->wf * p->hf < (1u << 30) && (size_t)p->wq * p->hq < (1u << 29), "image too large");
+	REQUIRE(ctx, is_mode(p->sample_mode), "unknown sample mode %d", p->sample_mode);
+	REQUIRE(ctx, p->grad_offset >= 0 && p->circle_radius >= 0 && p->blob_radius >= 0 && p->max_blobs >= 0, "negative radius/offset/max_blobs");
+	return VP_OK;
+}
+
+size_t raw_frame_bytes(const vp_params* p) { return (size_t)p->wq * p->hq * (size_t)vp_format_pixel_size(p->fmt); }
+
+/* blob list of `n` frames: prepare (whole call) + count + emit */
+int launch_blob_list(vp_ctx* ctx, const uint32_t* flat, const float* circ, int w, int h, int n, float thr, float min_score, int radius,
+                     int max_matches, int32_t* counter, int32_t* first_slot, int32_t* rowcount, uint8_t* matches, size_t match_stride)
+{
+	const int ns = need_score(thr, min_score);
+	k_peaks_count<<<dim3(cdiv(w, 256), h, n), 256, 0, ctx->stream>>>(flat, circ, w, h, thr, min_score, radius, ns, counter, rowcount);
+	int rc = check_launch(ctx, "k_peaks_count");
+	if (rc)
+		return rc;
+	k_peaks_emit<<<dim3(cdiv(h, 8), n), 256, 0, ctx->stream>>>(flat, circ, w, h, thr, min_score, radius, ns, max_matches, first_slot, rowcount,
+	                                                           matches, match_stride);
+	return check_launch(ctx, "k_peaks_emit");
+}
+
+/* single-launch fallback: recompute the SAT of flagged frames in the reference's sequential order */
+__global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
+                                                  const int* __restrict__ flag)
+{
+	if (flag[blockIdx.x] == 0)
+		return;
+	const size_t fbase = (size_t)blockIdx.x * w * h;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int y = warp; y < h; y += 32) { /* satHorizontal.cl:26-31 */
+		const size_t base = fbase + (size_t)y * w;
+		float sum = 0.f;
+		for (int x0 = 0; x0 < w; x0 += 32) {
+			const int x = x0 + lane;
+			const float val = x < w ? grad[base + x] : 0.f;
+			float mine = 0.f;
+			const int n = min(32, w - x0);
+			for (int k = 0; k < n; k++) {
+				sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, val, k));
+				if (lane == k)
+					mine = sum;
+			}
+			if (x < w)
+				hor[base + x] = mine;
+		}
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x < w; x += 1024) { /* satVertical.cl:26-31 */
+		float sum = 0.f;
+		for (int y = 0; y < h; y++) {
+			sum = __fadd_rn(sum, hor[fbase + (size_t)y * w + x]);
+			sat[fbase + (size_t)y * w + x] = sum;
+		}
+	}
+}
+
+int choose_group(vp_ctx* ctx, size_t nf, int n_frames)
+{
+	if (ctx->group > 0)
+		return ctx->group < n_frames ? ctx->group : n_frames;
+	/* keep raw + flat + grad + rowsum + sat + circ of one group (~24 B/px) well inside the 126 MB L2 */
+	size_t g = (size_t)(72u << 20) / (24 * nf);
+	if (g < 1) g = 1;
+	if (g > 8) g = 8;
+	return (int)g < n_frames ? (int)g : n_frames;
+}
+
+} // namespace
+
+/* =================================================================================================
+ * exported C ABI
+ * =============================================================================================== */
+extern "C" {
+
+const char* vp_version(void) { return "vp_b200 0.1 (sm_100a)"; }
+
+int vp_format_pixel_size(int fmt)
+{
+	switch (fmt) { /* opencl.cpp:24-31: stride * rowStride */
+	case VP_FMT_RGGB8:
+	case VP_FMT_GRBG8: return 4;
+	case VP_FMT_BGR8: return 3;
+	case VP_FMT_RGBA8: return 4;
+	case VP_FMT_U8: return 1;
+	case VP_FMT_F32: return 4;
+	case VP_FMT_NV12: return 2;
+	default: return 0;
+	}
+}
+
+int vp_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+const char* vp_last_error(const vp_ctx* ctx)
+{
+	(void)ctx;
+	return t_last_error.c_str();
+}
+
+int vp_ctx_create(int device, vp_ctx** out)
+{
+	if (!out)
+		return fail(nullptr, VP_ERR_INVALID, "out is null");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(nullptr, VP_ERR_NO_DEVICE, "no CUDA device: %s (there is no CPU fallback)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	}
+	if (device < 0 || device >= n)
+		return fail(nullptr, VP_ERR_INVALID, "device ordinal %d out of range [0,%d)", device, n);
+	CK(nullptr, cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(nullptr, cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+		return fail(nullptr, VP_ERR_UNSUPPORTED, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device, prop.name, prop.major, prop.minor);
+	vp_ctx* c = new vp_ctx();
+	c->device = device;
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess
+	    || cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
+		delete c;
+		return fail(nullptr, VP_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+	}
+	*out = c;
+	return VP_OK;
+}
+
+static void free_slots(vp_ctx* c)
+{
+	for (HostSlot& s : c->slots) {
+		cudaFree(s.raw); cudaFree(s.flat); cudaFree(s.grad); cudaFree(s.circ); cudaFree(s.matches); cudaFree(s.counter);
+		if (s.uploaded) cudaEventDestroy(s.uploaded);
+		if (s.computed) cudaEventDestroy(s.computed);
+		if (s.downloaded) cudaEventDestroy(s.downloaded);
+		s = HostSlot();
+	}
+	c->slot_frames = c->slot_raw = c->slot_nf = c->slot_blobs = 0;
+}
+
+void vp_ctx_destroy(vp_ctx* c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	cudaStreamSynchronize(c->copy_in);
+	cudaStreamSynchronize(c->copy_out);
+	for (LutEntry& e : c->luts)
+		cudaFree(e.d);
+	for (ProfEntry& p : c->prof) {
+		cudaEventDestroy(p.start);
+		cudaEventDestroy(p.stop);
+	}
+	cudaFree(c->rowsum); cudaFree(c->sat); cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
+	if (c->flag_host) cudaFreeHost(c->flag_host);
+	free_slots(c);
+	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->copy_in);
+	cudaStreamDestroy(c->copy_out);
+	delete c;
+}
+
+int vp_ctx_sync(vp_ctx* ctx)
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return VP_OK;
+}
+
+void* vp_ctx_stream(vp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t vp_launch_count(const vp_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group) /* tuning knob used by the benchmark sweep; 0 = automatic */
+{
+	REQUIRE(ctx, ctx && frames_per_group >= 0, "bad argument");
+	ctx->group = frames_per_group;
+	return VP_OK;
+}
+
+/* ---- profiling -------------------------------------------------------------------------------- */
+int vp_profiling_enable(vp_ctx* ctx, int on)
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->profiling = on != 0;
+	return VP_OK;
+}
+int vp_profiling_count(vp_ctx* ctx) { return ctx ? (int)ctx->prof.size() : 0; }
+int vp_profiling_get(vp_ctx* ctx, int i, const char** name, float* ms)
+{
+	REQUIRE(ctx, ctx && i >= 0 && i < (int)ctx->prof.size(), "profiling index out of range");
+	CK(ctx, cudaSetDevice(ctx->device));
+	ProfEntry& p = ctx->prof[i];
+	CK(ctx, cudaEventSynchronize(p.stop));
+	float t = 0.f;
+	CK(ctx, cudaEventElapsedTime(&t, p.start, p.stop));
+	if (name) *name = p.name;
+	if (ms) *ms = t;
+	return VP_OK;
+}
+int vp_profiling_clear(vp_ctx* ctx)
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	CK(ctx, cudaSetDevice(ctx->device));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	for (ProfEntry& p : ctx->prof) {
+		cudaEventDestroy(p.start);
+		cudaEventDestroy(p.stop);
+	}
+	ctx->prof.clear();
+	return VP_OK;
+}
+
+/* ---- buffers ---------------------------------------------------------------------------------- */
+int vp_buf_alloc(vp_ctx* ctx, size_t bytes, vp_buf** out)
+{
+	REQUIRE(ctx, ctx && out, "null argument");
+	*out = nullptr;
+	CK(ctx, cudaSetDevice(ctx->device));
+	vp_buf* b = new vp_buf();
+	b->ctx = ctx;
+	b->size = bytes;
+	const size_t alloc = bytes ? bytes : 1;
+	cudaError_t e = cudaMalloc(&b->d, alloc);
+	if (e == cudaSuccess)
+		e = cudaMallocHost(&b->h, alloc);
+	if (e != cudaSuccess) {
+		cudaFree(b->d);
+		delete b;
+		return fail(ctx, VP_ERR_NOMEM, "buffer allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+	}
+	*out = b;
+	return VP_OK;
+}
+
+int vp_buf_alloc_copy(vp_ctx* ctx, const void* host, size_t bytes, vp_buf** out)
+{
+	REQUIRE(ctx, host || bytes == 0, "host pointer is null");
+	int rc = vp_buf_alloc(ctx, bytes, out);
+	if (rc)
+		return rc;
+	if (bytes) {
+		memcpy((*out)->h, host, bytes);
+		CK(ctx, cudaMemcpyAsync((*out)->d, (*out)->h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+	}
+	return VP_OK;
+}
+
+int vp_buf_retain(vp_buf* b)
+{
+	if (!b) return fail(nullptr, VP_ERR_INVALID, "buf is null");
+	b->refs++;
+	return VP_OK;
+}
+
+int vp_buf_release(vp_buf* b)
+{
+	if (!b) return fail(nullptr, VP_ERR_INVALID, "buf is null");
+	if (--b->refs > 0)
+		return VP_OK;
+	cudaSetDevice(b->ctx->device);
+	cudaStreamSynchronize(b->ctx->stream);
+	cudaFree(b->d);
+	cudaFreeHost(b->h);
+	delete b;
+	return VP_OK;
+}
+
+int vp_buf_map(vp_buf* b, int mode, void** host)
+{
+	if (!b || !host) return fail(nullptr, VP_ERR_INVALID, "null argument");
+	vp_ctx* ctx = b->ctx;
+	REQUIRE(ctx, mode == VP_MAP_READ || mode == VP_MAP_WRITE || mode == VP_MAP_READWRITE, "bad map mode %d", mode);
+	std::lock_guard<std::mutex> l(b->mu);
+	REQUIRE(ctx, b->mapped == 0, "buffer is already mapped");
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (mode & VP_MAP_READ) { /* blocking read of everything enqueued so far (in-order queue, opencl.h:118) */
+		CK(ctx, cudaMemcpyAsync(b->h, b->d, b->size, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	b->mapped = mode;
+	*host = b->h;
+	return VP_OK;
+}
+
+int vp_buf_unmap(vp_buf* b)
+{
+	if (!b) return fail(nullptr, VP_ERR_INVALID, "buf is null");
+	vp_ctx* ctx = b->ctx;
+	std::lock_guard<std::mutex> l(b->mu);
+	REQUIRE(ctx, b->mapped != 0, "buffer is not mapped");
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (b->mapped & VP_MAP_WRITE) {
+		CK(ctx, cudaMemcpyAsync(b->d, b->h, b->size, cudaMemcpyHostToDevice, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream)); /* unmap waits, opencl.h:128-132 */
+	}
+	b->mapped = 0;
+	return VP_OK;
+}
+
+size_t vp_buf_size(const vp_buf* b) { return b ? b->size : 0; }
+void* vp_buf_device_ptr(vp_buf* b) { return b ? b->d : nullptr; }
+
+/* ---- images ----------------------------------------------------------------------------------- */
+int vp_img_alloc(vp_ctx* ctx, int fmt, int w, int h, vp_img** out)
+{
+	REQUIRE(ctx, ctx && out, "null argument");
+	*out = nullptr;
+	REQUIRE(ctx, fmt == VP_FMT_RGBA8 || fmt == VP_FMT_U8 || fmt == VP_FMT_F32, "format %d is not an image format", fmt);
+	REQUIRE(ctx, w >= 0 && h >= 0, "negative image size");
+	vp_buf* b = nullptr;
+	int rc = vp_buf_alloc(ctx, (size_t)w * h * vp_format_pixel_size(fmt), &b);
+	if (rc)
+		return rc;
+	vp_img* i = new vp_img();
+	i->ctx = ctx;
+	i->fmt = fmt;
+	i->w = w;
+	i->h = h;
+	i->buf = b;
+	*out = i;
+	return VP_OK;
+}
+
+int vp_img_retain(vp_img* i)
+{
+	if (!i) return fail(nullptr, VP_ERR_INVALID, "img is null");
+	i->refs++;
+	return VP_OK;
+}
+
+int vp_img_release(vp_img* i)
+{
+	if (!i) return fail(nullptr, VP_ERR_INVALID, "img is null");
+	if (--i->refs > 0)
+		return VP_OK;
+	vp_buf_release(i->buf);
+	delete i;
+	return VP_OK;
+}
+
+int vp_img_map(vp_img* i, int mode, void** host, size_t* byte_pitch)
+{
+	if (!i) return fail(nullptr, VP_ERR_INVALID, "img is null");
+	if (byte_pitch)
+		*byte_pitch = (size_t)i->w * vp_format_pixel_size(i->fmt); /* dense: CLImage::save indexes x + width*y (opencl.cpp:164-168) */
+	return vp_buf_map(i->buf, mode, host);
+}
+
+int vp_img_unmap(vp_img* i)
+{
+	if (!i) return fail(nullptr, VP_ERR_INVALID, "img is null");
+	return vp_buf_unmap(i->buf);
+}
+
+int vp_img_info(const vp_img* i, int* fmt, int* w, int* h)
+{
+	if (!i) return fail(nullptr, VP_ERR_INVALID, "img is null");
+	if (fmt) *fmt = i->fmt;
+	if (w) *w = i->w;
+	if (h) *h = i->h;
+	return VP_OK;
+}
+
+void* vp_img_device_ptr(vp_img* i) { return i ? i->buf->d : nullptr; }
+
+/* ---- stages ----------------------------------------------------------------------------------- */
+#define IMG_IS(img, f) ((img) && (img)->fmt == (f))
+#define SAME_SIZE(a, b) ((a)->w == (b)->w && (a)->h == (b)->h)
+
+static int check_planes(vp_ctx* ctx, vp_img* const ch[4], int fmt, int* wq, int* hq)
+{
+	REQUIRE(ctx, ch, "channel array is null");
+	const int n = fmt == VP_FMT_BGR8 ? 3 : 4;
+	for (int c = 0; c < n; c++) {
+		REQUIRE(ctx, IMG_IS(ch[c], VP_FMT_U8), "channel %d is not a U8 image", c);
+		REQUIRE(ctx, SAME_SIZE(ch[c], ch[0]), "channel %d size differs from channel 0", c);
+	}
+	*wq = ch[0]->w;
+	*hq = ch[0]->h;
+	return VP_OK;
+}
+
+static SrcPlanes planes_of(vp_img* const ch[4], int fmt)
+{
+	SrcPlanes s;
+	for (int c = 0; c < 4; c++)
+		s.ch[c] = (c == 3 && (fmt == VP_FMT_BGR8 || !ch[3])) ? (const uint8_t*)ch[0]->buf->d : (const uint8_t*)ch[c]->buf->d;
+	s.w = ch[0]->w;
+	return s;
+}
+
+int vp_raw2quad(vp_ctx* ctx, const vp_buf* raw, int fmt, int wq, int hq, vp_img* const ch[4])
+{
+	REQUIRE(ctx, ctx && raw, "null argument");
+	REQUIRE(ctx, is_raw_fmt(fmt), "format %d is not a raw format", fmt);
+	int w2, h2;
+	int rc = check_planes(ctx, ch, fmt, &w2, &h2);
+	if (rc) return rc;
+	REQUIRE(ctx, w2 == wq && h2 == hq && wq > 0 && hq > 0, "plane size %dx%d does not match %dx%d", w2, h2, wq, hq);
+	REQUIRE(ctx, raw->size >= (size_t)wq * hq * vp_format_pixel_size(fmt), "raw buffer too small");
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "raw2quad");
+	if (fmt == VP_FMT_BGR8) {
+		const int n = wq * hq;
+		k_raw2quad_bgr<<<cdiv(n, 256), 256, 0, ctx->stream>>>((const uint8_t*)raw->d, (uint8_t*)ch[0]->buf->d, (uint8_t*)ch[1]->buf->d,
+		                                                      (uint8_t*)ch[2]->buf->d, n);
+	} else {
+		k_raw2quad_bayer<<<dim3(cdiv(cdiv(wq, 4), 128), hq), 128, 0, ctx->stream>>>((const uint8_t*)raw->d, (uint8_t*)ch[0]->buf->d,
+		                                                                            (uint8_t*)ch[1]->buf->d, (uint8_t*)ch[2]->buf->d,
+		                                                                            (uint8_t*)ch[3]->buf->d, wq, hq);
+	}
+	return check_launch(ctx, "k_raw2quad");
+}
+
+int vp_resampling(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* flat, const vp_camera_model* model, float height, float scale,
+                  float offx, float offy, int mode)
+{
+	REQUIRE(ctx, ctx && model, "null argument");
+	REQUIRE(ctx, is_raw_fmt(fmt) && is_mode(mode), "bad format or sample mode");
+	int wq, hq;
+	int rc = check_planes(ctx, ch, fmt, &wq, &hq);
+	if (rc) return rc;
+	REQUIRE(ctx, IMG_IS(flat, VP_FMT_RGBA8), "flat is not an RGBA8 image");
+	if (flat->w == 0 || flat->h == 0)
+		return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	const float2* lut;
+	rc = get_lut(ctx, model, height, scale, offx, offy, flat->w, flat->h, &lut);
+	if (rc) return rc;
+	Stage st(ctx, "resampling");
+	return launch_reproject(ctx, planes_of(ch, fmt), 0, fmt, mode, lut, (uint32_t*)flat->buf->d, wq, hq, flat->w * flat->h, 1);
+}
+
+int vp_gradient_dot(vp_ctx* ctx, const vp_img* in, vp_img* out, int offset)
+{
+	REQUIRE(ctx, ctx && IMG_IS(in, VP_FMT_RGBA8) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(in, out), "gradient_dot needs RGBA8 in and F32 out of equal size");
+	if (in->w == 0 || in->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "gradientDot");
+	k_gradient_dot<<<dim3(cdiv(in->w, 64), cdiv(in->h, 4)), dim3(64, 4), 0, ctx->stream>>>((const uint32_t*)in->buf->d, (float*)out->buf->d, in->w, in->h, offset);
+	return check_launch(ctx, "k_gradient_dot");
+}
+
+int vp_sat_horizontal(vp_ctx* ctx, const vp_img* in, vp_img* out)
+{
+	REQUIRE(ctx, ctx && IMG_IS(in, VP_FMT_F32) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(in, out), "sat_horizontal needs F32 images of equal size");
+	if (in->w == 0 || in->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "satHorizontal");
+	k_sat_h_seq<<<dim3(cdiv(in->h, 8), 1), 256, 0, ctx->stream>>>((const float*)in->buf->d, (float*)out->buf->d, in->w, in->h, nullptr);
+	return check_launch(ctx, "k_sat_h_seq");
+}
+
+int vp_sat_vertical(vp_ctx* ctx, const vp_img* in, vp_img* out)
+{
+	REQUIRE(ctx, ctx && IMG_IS(in, VP_FMT_F32) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(in, out), "sat_vertical needs F32 images of equal size");
+	if (in->w == 0 || in->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "satVertical");
+	k_sat_v_seq<<<dim3(cdiv(in->w, 128), 1), 128, 0, ctx->stream>>>((const float*)in->buf->d, (float*)out->buf->d, in->w, in->h, nullptr);
+	return check_launch(ctx, "k_sat_v_seq");
+}
+
+int vp_circle(vp_ctx* ctx, const vp_img* sat, vp_img* out, int radius)
+{
+	REQUIRE(ctx, ctx && IMG_IS(sat, VP_FMT_F32) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(sat, out), "circle needs F32 images of equal size");
+	if (sat->w == 0 || sat->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "satBlobCenter");
+	k_circle<<<dim3(cdiv(sat->w, 64), cdiv(sat->h, 4), 1), 256, 0, ctx->stream>>>((const float*)sat->buf->d, (float*)out->buf->d, sat->w, sat->h, radius);
+	return check_launch(ctx, "k_circle");
+}
+
+int vp_blob_list(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_buf* matches, vp_buf* counter, float thr, float min_score, int radius,
+                 int max_matches)
+{
+	REQUIRE(ctx, ctx && IMG_IS(rgba, VP_FMT_RGBA8) && IMG_IS(circ, VP_FMT_F32) && SAME_SIZE(rgba, circ), "blob_list needs RGBA8 + F32 images of equal size");
+	REQUIRE(ctx, matches && counter && counter->size >= 12, "matches/counter buffers missing or counter smaller than 3 ints");
+	REQUIRE(ctx, radius >= 0 && max_matches >= 0 && matches->size >= (size_t)max_matches * 22, "matches buffer smaller than max_matches records");
+	if (rgba->w == 0 || rgba->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	int rc = ensure_scratch(ctx, 0, rgba->h, 1);
+	if (rc) return rc;
+	Stage st(ctx, "blobList", 3);
+	k_peaks_prepare<<<cdiv(rgba->h, 256), 256, 0, ctx->stream>>>((int32_t*)counter->d, ctx->first_slot, ctx->rowcount, rgba->h, 1, 0, nullptr);
+	rc = check_launch(ctx, "k_peaks_prepare");
+	if (rc) return rc;
+	return launch_blob_list(ctx, (const uint32_t*)rgba->buf->d, (const float*)circ->buf->d, rgba->w, rgba->h, 1, thr, min_score, radius, max_matches,
+	                        (int32_t*)counter->d, ctx->first_slot, ctx->rowcount, (uint8_t*)matches->d, 0);
+}
+
+static int check_nv12(vp_ctx* ctx, int w, int h, const vp_buf* nv12)
+{
+	REQUIRE(ctx, nv12, "nv12 buffer is null");
+	REQUIRE(ctx, (w % 2) == 0 && (h % 2) == 0, "NV12 needs even dimensions (Perspective.cpp:118-122), got %dx%d", w, h);
+	REQUIRE(ctx, nv12->size >= (size_t)w * h * 3 / 2, "nv12 buffer smaller than 1.5*w*h");
+	return VP_OK;
+}
+
+int vp_rgba2nv12_device(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_t* d_nv12)
+{
+	REQUIRE(ctx, ctx && d_rgba && d_nv12, "null argument");
+	REQUIRE(ctx, w >= 0 && h >= 0 && (w % 2) == 0 && (h % 2) == 0, "NV12 needs even dimensions, got %dx%d", w, h);
+	if (w == 0 || h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "rgba2nv12");
+	k_rgba2nv12<<<dim3(cdiv(w / 2, 256), h / 2), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h);
+	return check_launch(ctx, "k_rgba2nv12");
+}
+
+int vp_f2nv12_device(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_nv12)
+{
+	REQUIRE(ctx, ctx && d_f32 && d_nv12, "null argument");
+	REQUIRE(ctx, w >= 0 && h >= 0 && (w % 2) == 0 && (h % 2) == 0, "NV12 needs even dimensions, got %dx%d", w, h);
+	if (w == 0 || h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "f2nv12");
+	k_f2nv12<<<dim3(cdiv(w / 2, 256), h / 2), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h);
+	return check_launch(ctx, "k_f2nv12");
+}
+
+int vp_rgba2nv12(vp_ctx* ctx, const vp_img* rgba, vp_buf* nv12)
+{
+	REQUIRE(ctx, ctx && IMG_IS(rgba, VP_FMT_RGBA8), "rgba2nv12 needs an RGBA8 image");
+	int rc = check_nv12(ctx, rgba->w, rgba->h, nv12);
+	if (rc) return rc;
+	return vp_rgba2nv12_device(ctx, (const uint8_t*)rgba->buf->d, rgba->w, rgba->h, (uint8_t*)nv12->d);
+}
+
+int vp_f2nv12(vp_ctx* ctx, const vp_img* f32, vp_buf* nv12)
+{
+	REQUIRE(ctx, ctx && IMG_IS(f32, VP_FMT_F32), "f2nv12 needs an F32 image");
+	int rc = check_nv12(ctx, f32->w, f32->h, nv12);
+	if (rc) return rc;
+	return vp_f2nv12_device(ctx, (const float*)f32->buf->d, f32->w, f32->h, (uint8_t*)nv12->d);
+}
+
+int vp_quad2nv12(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_buf* nv12, int mode)
+{
+	REQUIRE(ctx, ctx && is_raw_fmt(fmt) && is_mode(mode), "bad format or sample mode");
+	int wq, hq;
+	int rc = check_planes(ctx, ch, fmt, &wq, &hq);
+	if (rc) return rc;
+	rc = check_nv12(ctx, wq, hq, nv12);
+	if (rc) return rc;
+	if (wq == 0 || hq == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "quad2nv12");
+	return launch_quad2nv12(ctx, planes_of(ch, fmt), fmt, mode, (uint8_t*)nv12->d, wq, hq);
+}
+
+int vp_quad2rgba(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* rgba, int mode)
+{
+	REQUIRE(ctx, ctx && is_raw_fmt(fmt) && is_mode(mode), "bad format or sample mode");
+	int wq, hq;
+	int rc = check_planes(ctx, ch, fmt, &wq, &hq);
+	if (rc) return rc;
+	REQUIRE(ctx, IMG_IS(rgba, VP_FMT_RGBA8) && rgba->w == wq && rgba->h == hq, "rgba image must be RGBA8 of the plane size");
+	if (wq == 0 || hq == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "quad2rgba");
+	return launch_quad2rgba(ctx, planes_of(ch, fmt), fmt, mode, (uint32_t*)rgba->buf->d, wq, hq);
+}
+
+static int raw_src_launch_nv12(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* out, int mode)
+{
+	if (fmt == VP_FMT_BGR8) {
+		SrcBGR s{ d_raw, wq };
+		return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq);
+	}
+	SrcBayer s{ d_raw, 2 * wq };
+	return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq);
+}
+
+int vp_raw2nv12_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_nv12, int mode)
+{
+	REQUIRE(ctx, ctx && d_raw && d_nv12 && is_raw_fmt(fmt) && is_mode(mode), "bad argument");
+	REQUIRE(ctx, wq >= 0 && hq >= 0 && (wq % 2) == 0 && (hq % 2) == 0, "NV12 needs even dimensions, got %dx%d", wq, hq);
+	if (wq == 0 || hq == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "raw2nv12");
+	return raw_src_launch_nv12(ctx, d_raw, fmt, wq, hq, d_nv12, mode);
+}
+
+int vp_raw2rgba_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_rgba, int mode)
+{
+	REQUIRE(ctx, ctx && d_raw && d_rgba && is_raw_fmt(fmt) && is_mode(mode), "bad argument");
+	REQUIRE(ctx, wq >= 0 && hq >= 0, "negative size");
+	if (wq == 0 || hq == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "raw2rgba");
+	if (fmt == VP_FMT_BGR8) {
+		SrcBGR s{ d_raw, wq };
+		return launch_quad2rgba(ctx, s, fmt, mode, (uint32_t*)d_rgba, wq, hq);
+	}
+	SrcBayer s{ d_raw, 2 * wq };
+	return launch_quad2rgba(ctx, s, fmt, mode, (uint32_t*)d_rgba, wq, hq);
+}
+
+int vp_circularize(vp_ctx* ctx, const vp_img* in, vp_img* out, int minr, int maxr)
+{
+	(void)minr; /* unused by blobCenter.cl as well */
+	REQUIRE(ctx, ctx && IMG_IS(in, VP_FMT_F32) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(in, out), "circularize needs F32 images of equal size");
+	if (in->w == 0 || in->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "blobCenter");
+	k_circularize<<<dim3(cdiv(in->w, 64), cdiv(in->h, 4)), 256, 0, ctx->stream>>>((const float*)in->buf->d, (float*)out->buf->d, in->w, in->h, maxr);
+	return check_launch(ctx, "k_circularize");
+}
+
+int vp_blob_score(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_img* out, float thr, int radius)
+{
+	REQUIRE(ctx, ctx && IMG_IS(rgba, VP_FMT_RGBA8) && IMG_IS(circ, VP_FMT_F32) && IMG_IS(out, VP_FMT_F32) && SAME_SIZE(rgba, circ) && SAME_SIZE(rgba, out),
+	        "blob_score needs RGBA8 + F32 in and F32 out of equal size");
+	REQUIRE(ctx, radius >= 0, "negative radius");
+	if (rgba->w == 0 || rgba->h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "blobScore");
+	k_blob_score<<<dim3(cdiv(rgba->w, 256), rgba->h), 256, 0, ctx->stream>>>((const uint32_t*)rgba->buf->d, (const float*)circ->buf->d, (float*)out->buf->d,
+	                                                                         rgba->w, rgba->h, thr, radius);
+	return check_launch(ctx, "k_blob_score");
+}
+
+/* ---- fused detection -------------------------------------------------------------------------- */
+int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* p, uint8_t* d_flat, float* d_grad, float* d_circ,
+                           vp_match* d_matches, int32_t* d_counter)
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	int rc = validate_params(ctx, p);
+	if (rc) return rc;
+	REQUIRE(ctx, n_frames >= 0, "negative frame count");
+	if (n_frames == 0) return VP_OK;
+	REQUIRE(ctx, d_raw && d_flat && d_grad && d_circ && d_counter && (d_matches || p->max_blobs == 0), "null device pointer");
+	CK(ctx, cudaSetDevice(ctx->device));
+	const int wf = p->wf, hf = p->hf;
+	const size_t nf = (size_t)wf * hf;
+	const size_t raw_bytes = raw_frame_bytes(p);
+	const int G = choose_group(ctx, nf, n_frames);
+	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames);
+	if (rc) return rc;
+	const float2* lut;
+	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, &lut);
+	if (rc) return rc;
+
+	cudaStream_t s = ctx->stream;
+	{
+		Stage st(ctx, "prepare");
+		const int n = n_frames * hf;
+		k_peaks_prepare<<<cdiv(n, 256), 256, 0, s>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag);
+		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
+	}
+	for (int f0 = 0; f0 < n_frames; f0 += G) {
+		const int g = n_frames - f0 < G ? n_frames - f0 : G;
+		uint32_t* flat = (uint32_t*)d_flat + (size_t)f0 * nf;
+		float* grad = d_grad + (size_t)f0 * nf;
+		float* circ = d_circ + (size_t)f0 * nf;
+		const uint8_t* raw = d_raw + (size_t)f0 * raw_bytes;
+		{
+			Stage st(ctx, "reproject");
+			if (p->fmt == VP_FMT_BGR8) {
+				SrcBGR src{ raw, p->wq };
+				rc = launch_reproject(ctx, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
+			} else {
+				SrcBayer src{ raw, 2 * p->wq };
+				rc = launch_reproject(ctx, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
+			}
+			if (rc) return rc;
+		}
+		{
+			Stage st(ctx, "grad_rowscan");
+			k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, ctx->rowsum, wf, hf, p->grad_offset, ctx->flag + f0);
+			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
+		}
+		{
+			Stage st(ctx, "colscan");
+			if ((rc = launch_colscan(ctx, ctx->rowsum, ctx->sat, wf, hf, g, ctx->flag + f0))) return rc;
+		}
+		{
+			Stage st(ctx, "sat_fix");
+			k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)ctx->rowsum, ctx->sat, wf, hf, ctx->flag + f0);
+			if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
+		}
+		{
+			Stage st(ctx, "circle");
+			k_circle<<<dim3(cdiv(wf, 64), cdiv(hf, 4), g), 256, 0, s>>>(ctx->sat, circ, wf, hf, p->circle_radius);
+			if ((rc = check_launch(ctx, "k_circle"))) return rc;
+		}
+		{
+			Stage st(ctx, "blob_list", 2);
+			rc = launch_blob_list(ctx, flat, circ, wf, hf, g, p->circ_threshold, p->min_score, p->blob_radius, p->max_blobs, d_counter + 3 * (size_t)f0,
+			                      ctx->first_slot + f0, ctx->rowcount + (size_t)f0 * hf, (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22,
+			                      (size_t)p->max_blobs * 22);
+			if (rc) return rc;
+		}
+	}
+	CK(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
+	ctx->last_fallbacks = -n_frames; /* negative: flag_host holds n flags not summed yet */
+	return VP_OK;
+}
+
+int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n)
+{
+	REQUIRE(ctx, ctx && n, "null argument");
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (ctx->last_fallbacks < 0) {
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		int cnt = 0;
+		for (int i = 0; i < -ctx->last_fallbacks; i++)
+			cnt += ctx->flag_host[i] != 0;
+		ctx->last_fallbacks = cnt;
+	}
+	*n = ctx->last_fallbacks;
+	return VP_OK;
+}
+
+static int ensure_slots(vp_ctx* ctx, size_t frames, size_t raw_bytes, size_t nf, size_t blobs)
+{
+	if (frames <= ctx->slot_frames && raw_bytes <= ctx->slot_raw && nf <= ctx->slot_nf && blobs <= ctx->slot_blobs)
+		return VP_OK;
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->copy_in));
+	CK(ctx, cudaStreamSynchronize(ctx->copy_out));
+	free_slots(ctx);
+	for (HostSlot& s : ctx->slots) {
+		CK(ctx, cudaMalloc(&s.raw, frames * raw_bytes));
+		CK(ctx, cudaMalloc(&s.flat, frames * nf * 4));
+		CK(ctx, cudaMalloc(&s.grad, frames * nf * 4));
+		CK(ctx, cudaMalloc(&s.circ, frames * nf * 4));
+		CK(ctx, cudaMalloc(&s.matches, frames * (blobs ? blobs : 1) * 22));
+		CK(ctx, cudaMalloc(&s.counter, frames * 12));
+		CK(ctx, cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
+		CK(ctx, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+		CK(ctx, cudaEventCreateWithFlags(&s.downloaded, cudaEventDisableTiming));
+	}
+	ctx->slot_frames = frames;
+	ctx->slot_raw = raw_bytes;
+	ctx->slot_nf = nf;
+	ctx->slot_blobs = blobs;
+	return VP_OK;
+}
+
+int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_params* p, vp_match* h_matches, int32_t* h_counter)
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	int rc = validate_params(ctx, p);
+	if (rc) return rc;
+	REQUIRE(ctx, n_frames >= 0, "negative frame count");
+	if (n_frames == 0) return VP_OK;
+	REQUIRE(ctx, h_raw && h_counter && (h_matches || p->max_blobs == 0), "null host pointer");
+	CK(ctx, cudaSetDevice(ctx->device));
+	const size_t nf = (size_t)p->wf * p->hf, raw_bytes = raw_frame_bytes(p), blobs = (size_t)p->max_blobs;
+	const int chunk = n_frames < 4 ? n_frames : 4; /* frames per upload: amortises launches, keeps latency low */
+	rc = ensure_slots(ctx, (size_t)chunk, raw_bytes, nf, blobs);
+	if (rc) return rc;
+	int k = 0;
+	for (int f0 = 0; f0 < n_frames; f0 += chunk, k++) {
+		const int g = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+		HostSlot& s = ctx->slots[k % HOST_SLOTS];
+		if (k >= HOST_SLOTS) { /* the slot's previous results must have left before it is overwritten */
+			CK(ctx, cudaStreamWaitEvent(ctx->copy_in, s.downloaded, 0));
+		}
+		CK(ctx, cudaMemcpyAsync(s.raw, h_raw + (size_t)f0 * raw_bytes, (size_t)g * raw_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+		CK(ctx, cudaEventRecord(s.uploaded, ctx->copy_in));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+		rc = vp_detect_batch_device(ctx, s.raw, g, p, s.flat, s.grad, s.circ, s.matches, s.counter);
+		if (rc) return rc;
+		CK(ctx, cudaEventRecord(s.computed, ctx->stream));
+		CK(ctx, cudaStreamWaitEvent(ctx->copy_out, s.computed, 0));
+		if (blobs)
+			CK(ctx, cudaMemcpyAsync((uint8_t*)h_matches + (size_t)f0 * blobs * 22, s.matches, (size_t)g * blobs * 22, cudaMemcpyDeviceToHost, ctx->copy_out));
+		CK(ctx, cudaMemcpyAsync(h_counter + 3 * (size_t)f0, s.counter, (size_t)g * 12, cudaMemcpyDeviceToHost, ctx->copy_out));
+		CK(ctx, cudaEventRecord(s.downloaded, ctx->copy_out));
+		ctx->last_flat = s.flat + (size_t)(g - 1) * nf * 4;
+		ctx->last_grad = s.grad + (size_t)(g - 1) * nf;
+		ctx->last_circ = s.circ + (size_t)(g - 1) * nf;
+	}
+	CK(ctx, cudaStreamSynchronize(ctx->copy_out));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return VP_OK;
+}
+
+int vp_detect_images(vp_ctx* ctx, const uint8_t** d_flat, const float** d_grad, const float** d_circ)
+{
+	REQUIRE(ctx, ctx && ctx->last_flat, "no vp_detect_host call has completed on this context");
+	if (d_flat) *d_flat = ctx->last_flat;
+	if (d_grad) *d_grad = ctx->last_grad;
+	if (d_circ) *d_circ = ctx->last_circ;
+	return VP_OK;
+}
+
+int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes)
+{
+	REQUIRE(ctx, ctx && (bytes == 0 || (host && dev)), "null argument");
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (bytes)
+		CK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return VP_OK;
+}
+
+int vp_copy_to_device(vp_ctx* ctx, void* dev, const void* host, size_t bytes)
+{
+	REQUIRE(ctx, ctx && (bytes == 0 || (host && dev)), "null argument");
+	CK(ctx, cudaSetDevice(ctx->device));
+	if (bytes)
+		CK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	return VP_OK;
+}
+
+int vp_host_alloc(size_t bytes, void** out)
+{
+	if (!out) return fail(nullptr, VP_ERR_INVALID, "out is null");
+	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+	if (e != cudaSuccess)
+		return fail(nullptr, VP_ERR_NOMEM, "pinned allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+	return VP_OK;
+}
+
+int vp_host_free(void* p)
+{
+	if (p && cudaFreeHost(p) != cudaSuccess)
+		return fail(nullptr, VP_ERR_CUDA, "cudaFreeHost failed");
+	return VP_OK;
+}
+
+} /* extern "C" */
