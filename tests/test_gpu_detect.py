@@ -37,6 +37,38 @@ def test_detect_single_frame(ctx, port, kw):
     assert want["max_abs_sat"] < 2 ** 24 and got["sat_fallbacks"] == 0
 
 
+@pytest.mark.parametrize("scale_mul,dx,dy", [(2.7, 0.0, 0.0), (0.37, 40.0, -25.0), (1.0, -900.0, 300.0), (1.0, 150.0, -700.0), (1.6, 5000.0, 0.0)])
+def test_detect_unusual_geometry(ctx, port, scale_mul, dx, dy):
+    """Flat tiles whose source footprint does not fit the staged tile (coarse scale), is tiny (fine scale), or lies
+    partly/entirely outside the sensor (shifted extent: CLAMP_TO_EDGE on whole tiles)."""
+    p, raw, _ = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=11)
+    p.field_scale *= scale_mul
+    p.off_x += dx
+    p.off_y += dy
+    want = port.detect(raw, p)
+    got = ctx.detect(raw, common.to_vp(p))
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+    ctx.set_staged_reproject(False)  # the direct-gather kernel must agree bit for bit
+    try:
+        direct = ctx.detect(raw, common.to_vp(p))
+    finally:
+        ctx.set_staged_reproject(True)
+    np.testing.assert_array_equal(direct["flat"], want["flat"])
+
+
+def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
+    """A camera in the field plane (rz == 0 for every pixel): coordinates are inf/NaN, every tap clamps or reads NaN -> 0."""
+    p, raw, _ = common.make_case(wq=96, hq=64)
+    p.model.c[2] = p.max_robot_height  # vz = 0 -> division by zero in field2image
+    want = port.detect(raw, p)
+    got = ctx.detect(raw, common.to_vp(p))
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    check_frame(got, 0, want)
+
+
 def test_detect_batch_of_distinct_frames(ctx, port):
     """11 frames (not a multiple of the upload chunk or the launch group), each with its own noise seed."""
     frames, wants = [], []

@@ -112,7 +112,7 @@ def test_blob_list(ctx, port, radius, min_score):
     got, gc = ctx.blob_list(rgba, circ, 15.0, min_score, radius, 2000)
     np.testing.assert_array_equal(gc, wc)
     common.assert_matches_equal(got, want, ordered=True)  # raster order, like the sequential oracle
-    assert len(want) > 10
+    assert len(want) >= (10 if min_score <= 0 else 1)
 
 
 def test_blob_list_overflow_and_negative_threshold(ctx, port):

@@ -21,6 +21,8 @@ from vpb200 import lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--group", type=int, default=0)
+ap.add_argument("--lanes", type=int, default=3)
+ap.add_argument("--direct", action="store_true", help="direct-gather reprojection instead of the staged kernel")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--times", action="store_true", help="print CUDA-event time per step and per stage")
@@ -41,6 +43,8 @@ d_c = torch.zeros((B, 3), dtype=torch.int32, device=dev)
 torch.cuda.synchronize()
 ctx = lib.Context(0)
 ctx.set_group(args.group)
+ctx.set_lanes(args.lanes)
+ctx.set_staged_reproject(not args.direct)
 
 
 def step():
@@ -60,7 +64,7 @@ e1.record(stream)
 t_issue = time.perf_counter() - t0
 e1.synchronize()
 ms = e0.elapsed_time(e1)
-print(f"batch {B} group {args.group}: {ms / args.steps / B * 1e3:.2f} us/frame, {B * args.steps / ms * 1e3:.0f} frames/s, "
+print(f"batch {B} group {args.group} lanes {args.lanes}: {ms / args.steps / B * 1e3:.2f} us/frame, {B * args.steps / ms * 1e3:.0f} frames/s, "
       f"cpu issue {t_issue / args.steps / B * 1e6:.2f} us/frame, counters[0]={d_c[0].tolist()}")
 if args.times:
     ctx.profiling(True)

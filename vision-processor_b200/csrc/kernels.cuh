@@ -16,6 +16,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 #include "vp_b200.h"
@@ -24,7 +25,11 @@ namespace vpk {
 
 constexpr int FMT_RGGB = VP_FMT_RGGB8, FMT_GRBG = VP_FMT_GRBG8, FMT_BGR = VP_FMT_BGR8;
 constexpr int MODE_RTE = VP_SAMPLE_BILINEAR_RTE, MODE_TRUNC = VP_SAMPLE_BILINEAR_TRUNC, MODE_NEAREST = VP_SAMPLE_NEAREST;
-constexpr int SAT_EXACT_LIMIT = 1 << 24; /* |integer| < 2^24 is exact in fp32 */
+/* Exactness bound of the fast path.  While every row sum and every SAT value stays below 2^22 in magnitude, the
+ * fp32 running sums of satHorizontal.cl / satVertical.cl are exact integers AND so is every intermediate of the
+ * four 4-tap box sums of satBlobCenter.cl:37-40 (|a-b| < 2^23, |a-b-c| < 2^23+2^22, |a-b-c+d| < 2^24), hence any
+ * summation order gives the reference's bits.  Frames that leave the bound are redone in the reference's order. */
+constexpr int SAT_EXACT_LIMIT = 1 << 22;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
@@ -119,6 +124,39 @@ __device__ __forceinline__ Axis axis_setup(float u, int n)
 	return ax;
 }
 
+/* The same axis for |u| < 2^20 without conversion-pipe instructions (FRND/F2I): rint via the 1.5*2^23 magic add,
+ * corrected to floor; the integer index comes out of the mantissa of the same add.  Bit-identical to axis_setup. */
+__device__ __forceinline__ Axis axis_setup_fast(float u, int n)
+{
+	constexpr float M = 12582912.0f; /* 1.5 * 2^23 */
+	Axis ax;
+	const float fu = __fsub_rn(u, 0.5f);
+	const float t = __fadd_rn(fu, M);
+	const float r = __fsub_rn(t, M); /* rint(fu) */
+	const bool dec = r > fu;
+	const float fi = dec ? __fsub_rn(r, 1.0f) : r; /* floor(fu) */
+	const int ii = __float_as_int(t) - 0x4B400000 - (dec ? 1 : 0);
+	ax.a = __fsub_rn(fu, fi);
+	ax.oma = __fsub_rn(1.0f, ax.a);
+	ax.i0 = min(max(ii, 0), n - 1);
+	ax.i1 = min(max(ii + 1, 0), n - 1);
+	return ax;
+}
+
+/* u8 -> fp32 without the conversion pipe: 0x4B000000 | b is the float 2^23 + b */
+__device__ __forceinline__ float u8_to_float(uint32_t b) { return __fsub_rn(__uint_as_float(0x4B000000u | b), 8388608.0f); }
+
+/* bilinear blend of four byte texels, MODE_RTE only: round-to-nearest-even happens in the 2^23 add */
+__device__ __forceinline__ uint32_t blend_rte(uint32_t b00, uint32_t b10, uint32_t b01, uint32_t b11, const Axis& x, const Axis& y)
+{
+	const float w00 = __fmul_rn(x.oma, y.oma), w10 = __fmul_rn(x.a, y.oma);
+	const float w01 = __fmul_rn(x.oma, y.a), w11 = __fmul_rn(x.a, y.a);
+	const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, u8_to_float(b00)), __fmul_rn(w10, u8_to_float(b10))), __fmul_rn(w01, u8_to_float(b01))),
+	                            __fmul_rn(w11, u8_to_float(b11)));
+	/* val is finite and in [0, 256): 2^23 + val rounds to nearest-even integer; saturate like the generic path */
+	return min(__float_as_uint(__fadd_rn(val, 8388608.0f)) - 0x4B000000u, 255u);
+}
+
 /* read_imageui(plane c, LINEAR|UNNORMALIZED|CLAMP_TO_EDGE, (u,v)).x */
 template <int MODE, class Src>
 __device__ __forceinline__ uint32_t sample(const Src& s, int c, const Axis& x, const Axis& y)
@@ -187,6 +225,9 @@ __device__ __forceinline__ uint32_t drgb(uint32_t r, uint32_t g, uint32_t b)
 	return dr | (dg << 8) | (db << 16) | 0xFF000000u;
 }
 
+template <class Src> struct SrcTraits { static constexpr bool is_bayer = false; };
+template <> struct SrcTraits<SrcBayer> { static constexpr bool is_bayer = true; };
+
 template <class Src>
 __device__ __forceinline__ Src src_frame(Src s, size_t byte_offset);
 template <>
@@ -202,7 +243,33 @@ __device__ __forceinline__ SrcBGR src_frame(SrcBGR s, size_t o) { s.raw += o; re
 
 /* ------------------------------------------------------------------------------------------------
  * K1 reproject: (raw2quad.cl:21-39 +) resampling.cl:52-99.  One flat pixel per thread, frame = blockIdx.y.
+ * Bayer + bilinear-RTE (the default) takes a fast path: texels are gathered straight from the raw frame with
+ * 32-bit offsets, all float<->int conversions are done with magic adds on the FMA/ALU pipes.  Coordinates that are
+ * not comfortably finite (|p| >= 2^20: only degenerate geometries) take the generic path, bit-identical by construction.
  * ---------------------------------------------------------------------------------------------- */
+template <int FMT>
+__device__ __forceinline__ uint32_t reproject_bayer_rte_fast(const uint8_t* __restrict__ raw, int wq, int hq, float px, float py)
+{
+	const Axis xp = axis_setup_fast(__fadd_rn(px, 0.25f), wq), xn = axis_setup_fast(__fsub_rn(px, 0.25f), wq);
+	const Axis yp = axis_setup_fast(__fadd_rn(py, 0.25f), hq), yn = axis_setup_fast(__fsub_rn(py, 0.25f), hq);
+	const uint32_t row = 2u * (uint32_t)wq;
+	/* byte offsets of quad (i, j): 2j*row + 2i; plane c adds (c/2)*row + c%2 */
+	const uint32_t yp0 = 2u * (uint32_t)yp.i0 * row, yp1 = 2u * (uint32_t)yp.i1 * row;
+	const uint32_t yn0 = 2u * (uint32_t)yn.i0 * row, yn1 = 2u * (uint32_t)yn.i1 * row;
+	const uint32_t xp0 = 2u * (uint32_t)xp.i0, xp1 = 2u * (uint32_t)xp.i1, xn0 = 2u * (uint32_t)xn.i0, xn1 = 2u * (uint32_t)xn.i1;
+	const uint8_t* p0 = raw;           /* plane 0 at (+,+) */
+	const uint8_t* p1 = raw + 1;       /* plane 1 at (-,+) */
+	const uint8_t* p2 = raw + row;     /* plane 2 at (+,-) */
+	const uint8_t* p3 = raw + row + 1; /* plane 3 at (-,-) */
+	const uint32_t v0 = blend_rte(__ldg(p0 + (yp0 + xp0)), __ldg(p0 + (yp0 + xp1)), __ldg(p0 + (yp1 + xp0)), __ldg(p0 + (yp1 + xp1)), xp, yp);
+	const uint32_t v1 = blend_rte(__ldg(p1 + (yp0 + xn0)), __ldg(p1 + (yp0 + xn1)), __ldg(p1 + (yp1 + xn0)), __ldg(p1 + (yp1 + xn1)), xn, yp);
+	const uint32_t v2 = blend_rte(__ldg(p2 + (yn0 + xp0)), __ldg(p2 + (yn0 + xp1)), __ldg(p2 + (yn1 + xp0)), __ldg(p2 + (yn1 + xp1)), xp, yn);
+	const uint32_t v3 = blend_rte(__ldg(p3 + (yn0 + xn0)), __ldg(p3 + (yn0 + xn1)), __ldg(p3 + (yn1 + xn0)), __ldg(p3 + (yn1 + xn1)), xn, yn);
+	if (FMT == FMT_RGGB)
+		return drgb(v0, v1 / 2 + v2 / 2, v3);
+	return drgb(v1, v0 / 2 + v3 / 2, v2);
+}
+
 template <int FMT, int MODE, class Src>
 __global__ void __launch_bounds__(256) k_reproject(Src src, size_t src_frame_stride, const float2* __restrict__ lut,
                                                     uint32_t* __restrict__ flat, int wq, int hq, int nf)
@@ -212,9 +279,223 @@ __global__ void __launch_bounds__(256) k_reproject(Src src, size_t src_frame_str
 		return;
 	const Src s = src_frame(src, (size_t)blockIdx.y * src_frame_stride);
 	const float2 pos = __ldg(lut + idx);
-	uint32_t r, g, b;
-	demosaic<FMT, MODE>(s, wq, hq, pos.x, pos.y, r, g, b);
-	flat[(size_t)blockIdx.y * nf + idx] = drgb(r, g, b);
+	uint32_t out;
+	if constexpr (MODE == MODE_RTE && FMT != FMT_BGR && SrcTraits<Src>::is_bayer) {
+		if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
+			out = reproject_bayer_rte_fast<FMT>(s.raw, wq, hq, pos.x, pos.y);
+		} else {
+			uint32_t r, g, b;
+			demosaic<FMT, MODE>(s, wq, hq, pos.x, pos.y, r, g, b);
+			out = drgb(r, g, b);
+		}
+	} else {
+		uint32_t r, g, b;
+		demosaic<FMT, MODE>(s, wq, hq, pos.x, pos.y, r, g, b);
+		out = drgb(r, g, b);
+	}
+	flat[(size_t)blockIdx.y * nf + idx] = out;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * K1, shared-memory staged form (Bayer, bilinear-RTE): the hot kernel of the fused path.
+ *
+ * The direct kernel above spends most of its issue slots on address arithmetic, clamps and u8->fp32 conversions of
+ * 16 gathered texels per pixel.  Here a CTA owns a 64x16 tile of the flat image; the quads its pixels can touch (known
+ * per camera geometry: k_tile_table) are staged ONCE into shared memory as four fp32 planes -- 16-byte coalesced loads
+ * of raw Bayer rows, de-interleaved and converted on the way in, edge texels replicated so that CLAMP_TO_EDGE needs no
+ * per-tap clamp -- and every tap becomes one LDS with an immediate offset.  Tiles whose footprint does not fit (extreme
+ * perspective) or whose coordinates are not finite fall back to the direct path pixel by pixel; results are identical.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int FT_W = 64, FT_H = 16;   /* flat tile */
+constexpr int TQ_W = 80, TQ_H = 24;   /* staged quads per plane (capacity) */
+
+struct TileEntry {
+	int ib, jb;     /* quad coordinate of staged texel (0,0); ib is a multiple of 8 */
+	int height;     /* staged quad rows needed (<= TQ_H) */
+	int flags;      /* bit 0: footprint fits and coordinates are finite; bit 1: no clamping needed and rows are 16-byte aligned */
+};
+
+/* floor(u - 0.5) exactly as axis_setup_fast computes it */
+__device__ __forceinline__ int axis_floor_fast(float u)
+{
+	constexpr float M = 12582912.0f;
+	const float fu = __fsub_rn(u, 0.5f);
+	const float t = __fadd_rn(fu, M);
+	const float r = __fsub_rn(t, M);
+	return __float_as_int(t) - 0x4B400000 - (r > fu ? 1 : 0);
+}
+
+/* once per geometry: footprint of every flat tile in quad coordinates */
+__global__ void __launch_bounds__(256) k_tile_table(const float2* __restrict__ lut, TileEntry* __restrict__ table, int wf, int hf, int wq, int hq)
+{
+	__shared__ int red[4][8];
+	const int tx = blockIdx.x, ty = blockIdx.y;
+	int imin = INT_MAX, imax = INT_MIN, jmin = INT_MAX, jmax = INT_MIN;
+	bool finite = true;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gx = tx * FT_W + (threadIdx.x & 63), gy = ty * FT_H + (threadIdx.x >> 6) + 4 * k;
+		if (gx < wf && gy < hf) {
+			const float2 pos = __ldg(lut + (size_t)gy * wf + gx);
+			if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
+				imin = min(imin, axis_floor_fast(__fsub_rn(pos.x, 0.25f)));
+				imax = max(imax, axis_floor_fast(__fadd_rn(pos.x, 0.25f)) + 1);
+				jmin = min(jmin, axis_floor_fast(__fsub_rn(pos.y, 0.25f)));
+				jmax = max(jmax, axis_floor_fast(__fadd_rn(pos.y, 0.25f)) + 1);
+			} else {
+				finite = false;
+			}
+		}
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+		imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+		jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o));
+		jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+	}
+	const int all_finite = __syncthreads_and(finite);
+	if ((threadIdx.x & 31) == 0) {
+		const int wp = threadIdx.x >> 5;
+		red[0][wp] = imin; red[1][wp] = imax; red[2][wp] = jmin; red[3][wp] = jmax;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < 8; k++) {
+			red[0][0] = min(red[0][0], red[0][k]); red[1][0] = max(red[1][0], red[1][k]);
+			red[2][0] = min(red[2][0], red[2][k]); red[3][0] = max(red[3][0], red[3][k]);
+		}
+		TileEntry e;
+		const int i0 = red[0][0], i1 = red[1][0], j0 = red[2][0], j1 = red[3][0];
+		const bool any = i0 <= i1 && j0 <= j1; /* false for an empty tile */
+		e.ib = any ? (i0 >= 0 ? i0 / 8 * 8 : -((-i0 + 7) / 8 * 8)) : 0;
+		e.jb = any ? j0 : 0;
+		e.height = any ? j1 - j0 + 1 : 0;
+		const bool fits = any && all_finite && (long long)i1 - e.ib + 1 <= TQ_W && e.height <= TQ_H;
+		const bool inner = fits && e.ib >= 0 && e.ib + TQ_W <= wq && e.jb >= 0 && e.jb + e.height <= hq && (wq % 8) == 0;
+		e.flags = (fits ? 1 : 0) | (inner ? 2 : 0);
+		table[ty * gridDim.x + tx] = e;
+	}
+}
+
+/* one bilinear sample from a staged plane: taps are immediate offsets from one address */
+__device__ __forceinline__ uint32_t blend_rte_staged(const float* __restrict__ t, float xa, float xoma, float ya, float yoma)
+{
+	const float w00 = __fmul_rn(xoma, yoma), w10 = __fmul_rn(xa, yoma), w01 = __fmul_rn(xoma, ya), w11 = __fmul_rn(xa, ya);
+	const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, t[0]), __fmul_rn(w10, t[1])), __fmul_rn(w01, t[TQ_W])), __fmul_rn(w11, t[TQ_W + 1]));
+	return min(__float_as_uint(__fadd_rn(val, 8388608.0f)) - 0x4B000000u, 255u);
+}
+
+/* tile-relative axis: index into the staged planes (no clamp: the edge texels are replicated in the tile) */
+__device__ __forceinline__ void axis_staged(float u, int origin_magic, int& ii, float& a, float& oma)
+{
+	constexpr float M = 12582912.0f;
+	const float fu = __fsub_rn(u, 0.5f);
+	const float t = __fadd_rn(fu, M);
+	const float r = __fsub_rn(t, M);
+	const bool dec = r > fu;
+	const float fi = dec ? __fsub_rn(r, 1.0f) : r;
+	ii = __float_as_int(t) - origin_magic - (dec ? 1 : 0);
+	a = __fsub_rn(fu, fi);
+	oma = __fsub_rn(1.0f, a);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+                                                           const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq, int wf,
+                                                           int hf, int tiles_x)
+{
+	__shared__ __align__(16) float T[4 * TQ_H * TQ_W];
+	const int tile = blockIdx.x;
+	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+	const uint8_t* raw = raw0 + (size_t)blockIdx.y * frame_stride;
+	uint32_t* out = flat + (size_t)blockIdx.y * wf * hf;
+	const TileEntry e = table[tile];
+	const int tid = threadIdx.x;
+	const int lx = tid & 63, ly = tid >> 6;
+	const int gx = tx * FT_W + lx;
+
+	if (!(e.flags & 1)) { /* footprint does not fit: direct gather */
+#pragma unroll 1
+		for (int k = 0; k < 4; k++) {
+			const int gy = ty * FT_H + ly + 4 * k;
+			if (gx < wf && gy < hf) {
+				const float2 pos = __ldg(lut + (size_t)gy * wf + gx);
+				uint32_t v;
+				if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
+					v = reproject_bayer_rte_fast<FMT>(raw, wq, hq, pos.x, pos.y);
+				} else {
+					uint32_t r, g, b;
+					const SrcBayer s{ raw, 2 * wq };
+					demosaic<FMT, MODE_RTE>(s, wq, hq, pos.x, pos.y, r, g, b);
+					v = drgb(r, g, b);
+				}
+				out[(size_t)gy * wf + gx] = v;
+			}
+		}
+		return;
+	}
+
+	const size_t row_bytes = 2 * (size_t)wq;
+	if (e.flags & 2) {
+		/* 16-byte vectors: raw row 2*jj + s holds planes (2s, 2s+1) of quad row jj interleaved */
+		constexpr int NV = TQ_W / 8;
+		const int total = NV * 2 * e.height;
+		const uint8_t* src = raw + (size_t)(2 * e.jb) * row_bytes + 2 * (size_t)e.ib;
+		for (int v = tid; v < total; v += 256) {
+			const int rr = v / NV, cv = v - rr * NV;
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)rr * row_bytes) + cv);
+			float* d0 = T + ((rr & 1) * 2 * TQ_H + (rr >> 1)) * TQ_W + cv * 8; /* plane 2s */
+			float* d1 = d0 + TQ_H * TQ_W;                                     /* plane 2s+1 */
+			const uint32_t wds[4] = { q.x, q.y, q.z, q.w };
+			float e0[8], e1[8];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				e0[2 * k] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7440)), 8388608.0f);
+				e1[2 * k] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7441)), 8388608.0f);
+				e0[2 * k + 1] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7442)), 8388608.0f);
+				e1[2 * k + 1] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7443)), 8388608.0f);
+			}
+			reinterpret_cast<float4*>(d0)[0] = make_float4(e0[0], e0[1], e0[2], e0[3]);
+			reinterpret_cast<float4*>(d0)[1] = make_float4(e0[4], e0[5], e0[6], e0[7]);
+			reinterpret_cast<float4*>(d1)[0] = make_float4(e1[0], e1[1], e1[2], e1[3]);
+			reinterpret_cast<float4*>(d1)[1] = make_float4(e1[4], e1[5], e1[6], e1[7]);
+		}
+	} else {
+		/* border tile: per-texel gather with the edge replicated (CLAMP_TO_EDGE resolved at staging time) */
+		const int total = 4 * e.height * TQ_W;
+		for (int v = tid; v < total; v += 256) {
+			const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
+			const int jj = rc >> 2, c = rc & 3;
+			const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
+			const uint32_t b = __ldg(raw + (size_t)(2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1));
+			T[(c * TQ_H + jj) * TQ_W + ii] = u8_to_float(b);
+		}
+	}
+	__syncthreads();
+
+	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gy = ty * FT_H + ly + 4 * k;
+		if (gx < wf && gy < hf) {
+			const float2 pos = __ldg(lut + (size_t)gy * wf + gx);
+			int ixp, ixn, iyp, iyn;
+			float axp, oxp, axn, oxn, ayp, oyp, ayn, oyn;
+			axis_staged(__fadd_rn(pos.x, 0.25f), xmagic, ixp, axp, oxp);
+			axis_staged(__fsub_rn(pos.x, 0.25f), xmagic, ixn, axn, oxn);
+			axis_staged(__fadd_rn(pos.y, 0.25f), ymagic, iyp, ayp, oyp);
+			axis_staged(__fsub_rn(pos.y, 0.25f), ymagic, iyn, ayn, oyn);
+			const float* rowp = T + iyp * TQ_W;
+			const float* rown = T + iyn * TQ_W;
+			/* plane 0 at (+,+), 1 at (-,+), 2 at (+,-), 3 at (-,-)  (resampling.cl:65-80) */
+			const uint32_t v0 = blend_rte_staged(rowp + ixp, axp, oxp, ayp, oyp);
+			const uint32_t v1 = blend_rte_staged(rowp + TQ_H * TQ_W + ixn, axn, oxn, ayp, oyp);
+			const uint32_t v2 = blend_rte_staged(rown + 2 * TQ_H * TQ_W + ixp, axp, oxp, ayn, oyn);
+			const uint32_t v3 = blend_rte_staged(rown + 3 * TQ_H * TQ_W + ixn, axn, oxn, ayn, oyn);
+			out[(size_t)gy * wf + gx] = FMT == FMT_RGGB ? drgb(v0, v1 / 2 + v2 / 2, v3) : drgb(v1, v0 / 2 + v3 / 2, v2);
+		}
+	}
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -565,12 +846,44 @@ __device__ __forceinline__ int peak_class(const uint32_t* __restrict__ img, cons
 	return 3;
 }
 
-/* scratch layout per frame: [0] initial counter[0] (first output slot), then hf row counts */
-/* pass A: classify every pixel, count blobs per row, accumulate counter[0..2].
- * CTA = 8 rows x 32 columns?  No: one warp = 32 consecutive pixels of a row, 8 warps = 256 pixels of one row. */
+/* Compaction scratch (per frame): rowcount[hf] = blobs per row, masks[hf][ceil(wf/32)] = one bit per blob pixel.
+ * Pass A (k_circ_peaks on the fused path, k_peaks_count for the stage API) classifies every pixel once, writes the
+ * bit masks, counts blobs per row and accumulates counter[0..2]; pass B (k_peaks_emit) ranks the set bits in raster
+ * order (first slot + blobs of earlier rows + blobs to the left) and writes the records with rank < max_matches. */
+
+/* publish one warp's classification of 32 consecutive pixels of row y (segment index seg) */
+__device__ __forceinline__ void publish_segment(int cls, int lane, bool seg_valid, int32_t* __restrict__ rowcount_f, uint32_t* __restrict__ masks_f,
+                                                int wpr, int y, int seg, int& n_blob, int& n_score, int& n_peak)
+{
+	const unsigned m3 = __ballot_sync(0xffffffffu, cls == 3);
+	const unsigned m2 = __ballot_sync(0xffffffffu, cls == 2);
+	const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1);
+	if (lane == 0 && seg_valid) {
+		masks_f[(size_t)y * wpr + seg] = m3;
+		if (m3)
+			atomicAdd(rowcount_f + y, __popc(m3));
+	}
+	n_blob += __popc(m3);
+	n_score += __popc(m2);
+	n_peak += __popc(m1);
+}
+
+__device__ __forceinline__ void publish_counters(int lane, int32_t* __restrict__ counter_f, int n_blob, int n_score, int n_peak)
+{
+	if (lane == 0) {
+		if (n_blob)
+			atomicAdd(counter_f + 0, n_blob); /* blobList.cl:87 counts past maxMatches too */
+		if (n_score)
+			atomicAdd(counter_f + 1, n_score); /* :80 */
+		if (n_peak)
+			atomicAdd(counter_f + 2, n_peak); /* :53 */
+	}
+}
+
+/* stage API pass A: a warp = 32 consecutive pixels of a row (x0 multiple of 32) */
 __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h,
                                                      float thr, float min_score, int radius, int need_score,
-                                                     int32_t* __restrict__ counter, int32_t* __restrict__ rowcount)
+                                                     int32_t* __restrict__ counter, int32_t* __restrict__ rowcount, uint32_t* __restrict__ masks, int wpr)
 {
 	const int x = blockIdx.x * 256 + threadIdx.x;
 	const int y = blockIdx.y;
@@ -581,25 +894,149 @@ __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict_
 		PeakCtx p;
 		cls = peak_class(img + fbase, circ + fbase, w, h, x, y, thr, min_score, radius, need_score != 0, p);
 	}
-	const unsigned m3 = __ballot_sync(0xffffffffu, cls == 3);
-	const unsigned m2 = __ballot_sync(0xffffffffu, cls == 2);
-	const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1);
-	if ((threadIdx.x & 31) == 0) {
-		if (m3) {
-			atomicAdd(rowcount + (size_t)f * h + y, __popc(m3));
-			atomicAdd(counter + 3 * f + 0, __popc(m3)); /* blobList.cl:87 counts past maxMatches too */
+	int nb = 0, ns = 0, np = 0;
+	publish_segment(cls, threadIdx.x & 31, (x & ~31) < w, rowcount + (size_t)f * h, masks + (size_t)f * h * wpr, wpr, y, x >> 5, nb, ns, np);
+	publish_counters(threadIdx.x & 31, counter + 3 * f, nb, ns, np);
+}
+
+/* K3 (fused path): circularity (satBlobCenter.cl:22-42) + peak classification (blobList.cl:38-81) of a 64x32 tile,
+ * specialised on the radius R so that every tile dimension and tap offset is an immediate.
+ * Away from the image border and inside the exactness bound each quadrant score is a box sum
+ *   Q(u,v) = S(u+k,v+k) - S(u+k,v) - S(u,v+k) + S(u,v),  k = R-1:
+ *   pp(x,y) = Q(x+1,y+1), nn = Q(x-R,y-R), pn = -Q(x+1,y-R), np = -Q(x-R,y+1)
+ * so one shared Q map (4 SAT taps per entry, each SAT value loaded ~2.7 times per entry from L1/L2 by walking down a
+ * column with a register window) replaces 16 taps per pixel.  Every intermediate is an exact integer below 2^24, so the
+ * bits equal the reference's left-to-right evaluation, and the division by R*R is done with the exact 3-operation
+ * sequence q0 = m*y, e = fma(-q0,d,m), q = fma(e,y,q0) (y = RN(1/d)), which is the correctly rounded quotient for all
+ * |m| <= 2^24, d = R*R, R <= 24 (tests/test_exact_division.py checks every case).  Border pixels and flagged frames use
+ * the literal 16-tap form with IEEE division.  Circularities of the tile plus a 1-pixel ring stay in shared memory for
+ * the 4-neighbour peak test. */
+constexpr int CT_W = 64, CT_H = 32;
+constexpr int CIRC_PEAKS_MAX_R = 12;
+
+/* blobList.cl:79 for the (non-default) case that the score can reject: kept out of line, it is never hot */
+__device__ __noinline__ int classify_by_score(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, float c, float min_score)
+{
+	return blob_score(disc_stats(img, w, h, x, y, radius), c) < min_score ? 2 : 3;
+}
+
+__device__ __noinline__ float circle_px_generic(const float* __restrict__ sat, int w, int h, int x, int y, int r)
+{
+	return circle_px(sat, w, h, x, y, r, (float)(r * r));
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
+                                                    int w, int h, float thr, float min_score, int radius, int need_score,
+                                                    const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                                                    uint32_t* __restrict__ masks, int wpr)
+{
+	constexpr int K = R - 1;
+	constexpr int QW = CT_W + R + 3, QH = CT_H + R + 3; /* Q map: u in [x0-1-R, x0+CT_W+1] */
+	constexpr int CW = CT_W + 2, CH = CT_H + 2;         /* circularity: x in [x0-1, x0+CT_W] */
+	constexpr int NRG = 256 / QW;                       /* row groups walking down the Q columns */
+	constexpr int RPG = (QH + NRG - 1) / NRG;
+	__shared__ float Q[QH * QW];
+	__shared__ float Cc[CH * CW];
+	const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H, f = blockIdx.z;
+	const size_t fbase = (size_t)f * w * h;
+	const float* satf = sat + fbase;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const bool flagged = flag[f] != 0;
+	const int qx0 = x0 - 1 - R, qy0 = y0 - 1 - R;
+	/* every SAT tap of every Q entry and every pixel of the ring lies inside the image: no clamping in this CTA */
+	const bool inner = qx0 >= 0 && x0 + CT_W + R <= w - 1 && qy0 >= 0 && y0 + CT_H + R <= h - 1;
+
+	if (!flagged) {
+		const int g = tid / QW, i = tid - g * QW;
+		if (g < NRG) {
+			const int j0 = g * RPG;
+			float a[RPG + K], b[RPG + K];
+			if (inner) {
+				const float* p = satf + (size_t)(qy0 + j0) * w + (qx0 + i);
+#pragma unroll
+				for (int j = 0; j < RPG + K; j++) {
+					const bool ok = j0 + j < QH + K;
+					a[j] = ok ? __ldg(p + (size_t)j * w) : 0.f;
+					b[j] = ok ? __ldg(p + (size_t)j * w + K) : 0.f;
+				}
+			} else {
+				const int xa = clampi(qx0 + i, 0, w - 1), xb = clampi(qx0 + i + K, 0, w - 1);
+#pragma unroll
+				for (int j = 0; j < RPG + K; j++) {
+					const float* row = satf + (size_t)clampi(qy0 + j0 + j, 0, h - 1) * w;
+					a[j] = __ldg(row + xa);
+					b[j] = __ldg(row + xb);
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < RPG; j++)
+				if (j0 + j < QH)
+					Q[(j0 + j) * QW + i] = __fadd_rn(__fsub_rn(__fsub_rn(b[j + K], b[j]), a[j + K]), a[j]);
 		}
-		if (m2)
-			atomicAdd(counter + 3 * f + 1, __popc(m2)); /* :80 */
-		if (m1)
-			atomicAdd(counter + 3 * f + 2, __popc(m1)); /* :53 */
 	}
+	__syncthreads();
+
+	constexpr float D = (float)(R * R);
+	constexpr float Y = 1.0f / D; /* correctly rounded reciprocal */
+	for (int idx = tid; idx < CW * CH; idx += 256) {
+		const int cj = idx / CW, ci = idx - cj * CW;
+		const int px = x0 - 1 + ci, py = y0 - 1 + cj;
+		int cx = px, cy = py;
+		bool fast = !flagged;
+		if (!inner) {
+			cx = clampi(px, 0, w - 1);
+			cy = clampi(py, 0, h - 1);
+			fast = fast && cx - R >= 0 && cx + R <= w - 1 && cy - R >= 0 && cy + R <= h - 1;
+		}
+		float c;
+		if (fast) {
+			/* Q index of image coordinate u is u - (x0-1-R): Q(cx-R, .) sits at cx-(x0-1), Q(cx+1, .) R+1 further */
+			const float* q = Q + (cy - (y0 - 1)) * QW + (cx - (x0 - 1));
+			const float pp = q[(R + 1) * QW + (R + 1)];
+			const float nn = q[0];
+			const float pn = __fsub_rn(0.0f, q[R + 1]);        /* 0 - Q keeps +0 where the reference's last addition yields +0 */
+			const float np = __fsub_rn(0.0f, q[(R + 1) * QW]);
+			const float m = fminf(fminf(pp, nn), fminf(pn, np));
+			const float q0 = __fmul_rn(m, Y);
+			c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0); /* == m / D, satBlobCenter.cl:41 */
+		} else {
+			c = circle_px_generic(satf, w, h, cx, cy, R);
+		}
+		Cc[idx] = c;
+		if (ci >= 1 && ci <= CT_W && cj >= 1 && cj <= CT_H && px < w && py < h)
+			circ_out[fbase + (size_t)py * w + px] = c;
+	}
+	__syncthreads();
+
+	/* peak classification: warp -> 4 rows x 2 segments of 32 pixels */
+	int nb = 0, ns = 0, npk = 0;
+	int32_t* rc = rowcount + (size_t)f * h;
+	uint32_t* mk = masks + (size_t)f * h * wpr;
+#pragma unroll 1
+	for (int q = 0; q < 8; q++) {
+		const int ty = warp * 4 + (q >> 1), tx = (q & 1) * 32 + lane;
+		const int x = x0 + tx, y = y0 + ty;
+		int cls = 0;
+		if (x < w && y < h) {
+			const float* cc = Cc + (ty + 1) * CW + tx + 1;
+			const float c = cc[0];
+			if (!(c < thr)) { /* blobList.cl:39 */
+				if (cc[-1] > c || cc[1] > c || cc[-CW] > c || cc[CW] > c) /* :47-55; the ring holds the clamped neighbours */
+					cls = 1;
+				else
+					cls = need_score ? classify_by_score(flat + fbase, w, h, x, y, radius, c, min_score) : 3; /* :79 */
+			}
+		}
+		publish_segment(cls, lane, y < h && x0 + (q & 1) * 32 < w, rc, mk, wpr, y < h ? y : 0, (x0 >> 5) + (q & 1), nb, ns, npk);
+	}
+	publish_counters(lane, counter + 3 * f, nb, ns, npk);
 }
 
 __device__ __forceinline__ void store_match(uint8_t* __restrict__ dst, float mx, float my, const uint32_t color[3], uint32_t center, float circ,
                                             float score)
 {
-	/* 22-byte packed record, 2-byte aligned: ten 16-bit stores + two bytes would do; keep it simple and sparse */
+	/* 22-byte packed record, 2-byte aligned: eleven 16-bit stores (sparse: a few hundred records per frame) */
 	uint16_t* d = reinterpret_cast<uint16_t*>(dst);
 	const uint32_t ux = __float_as_uint(mx), uy = __float_as_uint(my), uc = __float_as_uint(circ), us = __float_as_uint(score);
 	d[0] = (uint16_t)ux; d[1] = (uint16_t)(ux >> 16);
@@ -611,12 +1048,63 @@ __device__ __forceinline__ void store_match(uint8_t* __restrict__ dst, float mx,
 	d[9] = (uint16_t)us; d[10] = (uint16_t)(us >> 16);
 }
 
-/* pass B: one warp per row that holds at least one blob: rank = first slot + blobs of earlier rows + blobs to the
- * left in this row; the record is written only if rank < max_matches (blobList.cl:88). */
-__global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h,
-                                                    float thr, float min_score, int radius, int need_score, int max_matches,
-                                                    const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
-                                                    uint8_t* __restrict__ matches, size_t match_frame_stride)
+/* disc statistics of one blob computed by the whole warp: lane = dx, loop over dy (blobList.cl:63-72) */
+__device__ __forceinline__ DiscStats disc_stats_warp(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, int lane)
+{
+	DiscStats d;
+	d.n = 0;
+	d.s1[0] = d.s1[1] = d.s1[2] = d.s2[0] = d.s2[1] = d.s2[2] = 0;
+	const int sq = radius * radius;
+	for (int dx0 = -radius; dx0 <= radius; dx0 += 32) {
+		const int dx = dx0 + lane;
+		if (dx <= radius) {
+			const int xx = clampi(x + dx, 0, w - 1);
+			for (int dy = -radius; dy <= radius; dy++)
+				if (dx * dx + dy * dy <= sq) {
+					const uint32_t v = __ldg(img + (size_t)clampi(y + dy, 0, h - 1) * w + xx);
+#pragma unroll
+					for (int k = 0; k < 3; k++) {
+						const uint32_t c = (v >> (8 * k)) & 255u;
+						d.s1[k] += c;
+						d.s2[k] += c * c;
+					}
+					d.n++;
+				}
+		}
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) {
+		d.n += __shfl_xor_sync(0xffffffffu, d.n, o);
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			d.s1[k] += __shfl_xor_sync(0xffffffffu, d.s1[k], o);
+			d.s2[k] += __shfl_xor_sync(0xffffffffu, d.s2[k], o);
+		}
+	}
+	return d;
+}
+
+/* the record of one blob pixel, blobList.cl:83-101; called by a full warp, lane 0 stores */
+__device__ __forceinline__ void emit_match(const uint32_t* __restrict__ im, const float* __restrict__ ci, int w, int h, int x, int y, int radius,
+                                           uint8_t* __restrict__ dst, int lane)
+{
+	const DiscStats d = disc_stats_warp(im, w, h, x, y, radius, lane);
+	if (lane != 0)
+		return;
+	const float c = __ldg(ci + (size_t)y * w + x);
+	const float cnx = __ldg(ci + (size_t)y * w + max(x - 1, 0)), cpx = __ldg(ci + (size_t)y * w + min(x + 1, w - 1));
+	const float cny = __ldg(ci + (size_t)max(y - 1, 0) * w + x), cpy = __ldg(ci + (size_t)min(y + 1, h - 1) * w + x);
+	const float score = blob_score(d, c);
+	const float mx = __fadd_rn((float)x, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cnx, cpx)), __fadd_rn(__fsub_rn(cnx, __fmul_rn(2.0f, c)), cpx))); /* :93 */
+	const float my = __fadd_rn((float)y, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cny, cpy)), __fadd_rn(__fsub_rn(cny, __fmul_rn(2.0f, c)), cpy))); /* :94 */
+	const uint32_t color[3] = { d.s1[0] / (uint32_t)d.n, d.s1[1] / (uint32_t)d.n, d.s1[2] / (uint32_t)d.n }; /* :85 */
+	store_match(dst, mx, my, color, __ldg(im + (size_t)y * w + x), c, score);
+}
+
+/* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp */
+__global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h, int radius,
+                                                    int max_matches, const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
+                                                    const uint32_t* __restrict__ masks, int wpr, uint8_t* __restrict__ matches, size_t match_frame_stride)
 {
 	const int lane = threadIdx.x & 31;
 	const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -632,35 +1120,24 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 #pragma unroll
 	for (int d = 16; d; d >>= 1)
 		before += __shfl_xor_sync(0xffffffffu, before, d);
-	int rank0 = first_slot[f] + before;
-	if (rank0 >= max_matches)
-		return;
+	int rank = first_slot[f] + before;
 	const size_t fbase = (size_t)f * w * h;
-	const uint32_t* im = img + fbase;
-	const float* ci = circ + fbase;
+	const uint32_t* mk = masks + ((size_t)f * h + y) * wpr;
 	uint8_t* out = matches + (size_t)f * match_frame_stride;
-	for (int x0 = 0; x0 < w && rank0 < max_matches; x0 += 32) {
-		const int x = x0 + lane;
-		int cls = 0;
-		PeakCtx p;
-		if (x < w)
-			cls = peak_class(im, ci, w, h, x, y, thr, min_score, radius, need_score != 0, p);
-		const unsigned m = __ballot_sync(0xffffffffu, cls == 3);
-		if (cls == 3) {
-			const int rank = rank0 + __popc(m & ((1u << lane) - 1u));
-			if (rank < max_matches) {
-				const DiscStats d = disc_stats(im, w, h, x, y, radius);
-				const float score = blob_score(d, p.c);
-				/* blobList.cl:93-94 */
-				const float mx = __fadd_rn((float)x, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(p.cnx, p.cpx)),
-				                                              __fadd_rn(__fsub_rn(p.cnx, __fmul_rn(2.0f, p.c)), p.cpx)));
-				const float my = __fadd_rn((float)y, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(p.cny, p.cpy)),
-				                                              __fadd_rn(__fsub_rn(p.cny, __fmul_rn(2.0f, p.c)), p.cpy)));
-				const uint32_t color[3] = { d.s1[0] / (uint32_t)d.n, d.s1[1] / (uint32_t)d.n, d.s1[2] / (uint32_t)d.n }; /* :85 */
-				store_match(out + 22 * (size_t)rank, mx, my, color, __ldg(im + (size_t)y * w + x), p.c, score);
+	for (int base = 0; base < wpr && rank < max_matches; base += 32) {
+		const uint32_t mine = base + lane < wpr ? mk[base + lane] : 0u;
+		unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+		while (nz && rank < max_matches) {
+			const int src = __ffs(nz) - 1;
+			nz &= nz - 1;
+			uint32_t word = __shfl_sync(0xffffffffu, mine, src);
+			while (word && rank < max_matches) {
+				const int b = __ffs(word) - 1;
+				word &= word - 1;
+				emit_match(img + fbase, circ + fbase, w, h, (base + src) * 32 + b, y, radius, out + 22 * (size_t)rank, lane);
+				rank++;
 			}
 		}
-		rank0 += __popc(m);
 	}
 }
 

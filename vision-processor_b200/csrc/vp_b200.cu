@@ -22,8 +22,9 @@ namespace {
 thread_local std::string t_last_error;
 
 struct LutEntry {
-	uint8_t key[96];
+	uint8_t key[104];
 	float2* d = nullptr;
+	TileEntry* tiles = nullptr; /* footprint of every 64x16 flat tile (k_tile_table) */
 	uint64_t stamp = 0;
 };
 
@@ -58,15 +59,22 @@ struct vp_ctx {
 	std::vector<LutEntry> luts;
 	uint64_t lut_clock = 0;
 
-	/* scratch of the fused path, sized for `group` frames of nf pixels / hf rows */
-	int32_t* rowsum = nullptr;
-	float* sat = nullptr;
+	/* scratch of the fused path: per lane (stream) `group` frames of row sums and SAT */
+	static constexpr int MAX_LANES = 4;
+	cudaStream_t lane_stream[MAX_LANES] = {}; /* [0] aliases `stream` */
+	cudaEvent_t lane_done[MAX_LANES] = {};
+	cudaEvent_t fork = nullptr;
+	int lanes = 3;
+	int32_t* rowsum[MAX_LANES] = {};
+	float* sat[MAX_LANES] = {};
 	size_t scratch_px = 0;
 	int32_t* rowcount = nullptr;
+	uint32_t* masks = nullptr; /* one bit per pixel: blob pixels of the current call */
 	int32_t* first_slot = nullptr;
 	int* flag = nullptr;
-	size_t rows_cap = 0, frames_cap = 0;
+	size_t rows_cap = 0, frames_cap = 0, mask_words_cap = 0;
 	int group = 0; /* 0 = choose from the frame size */
+	bool staged_reproject = true;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
 
@@ -131,7 +139,8 @@ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 struct Stage {
 	vp_ctx* c;
 	int idx = -1;
-	Stage(vp_ctx* ctx, const char* name, int n_launches = 1): c(ctx)
+	cudaStream_t s;
+	Stage(vp_ctx* ctx, const char* name, int n_launches = 1, cudaStream_t on = nullptr): c(ctx), s(on ? on : ctx->stream)
 	{
 		c->launches += (uint64_t)n_launches;
 		if (c->profiling) {
@@ -140,7 +149,7 @@ struct Stage {
 			ProfEntry e{ name, nullptr, nullptr };
 			cudaEventCreate(&e.start);
 			cudaEventCreate(&e.stop);
-			cudaEventRecord(e.start, c->stream);
+			cudaEventRecord(e.start, s);
 			c->prof.push_back(e);
 			idx = (int)c->prof.size() - 1;
 		}
@@ -148,7 +157,7 @@ struct Stage {
 	~Stage()
 	{
 		if (idx >= 0)
-			cudaEventRecord(c->prof[idx].stop, c->stream);
+			cudaEventRecord(c->prof[idx].stop, s);
 	}
 };
 
@@ -171,10 +180,12 @@ bool is_mode(int m) { return m == VP_SAMPLE_BILINEAR_RTE || m == VP_SAMPLE_BILIN
 	default: { constexpr int MODE = MODE_NEAREST; constexpr int FMTC = FMT; CALL; } break;                             \
 	}
 
-/* coordinate table of a geometry, cached per context (a handful of geometries at most: one per camera) */
-int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, float offx, float offy, int wf, int hf, const float2** out)
+/* coordinate table of a geometry (plus the tile footprints for a wq x hq source), cached per context: a handful of
+ * geometries at most, one per camera */
+int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, float offx, float offy, int wf, int hf, int wq, int hq,
+            const float2** out, const TileEntry** tiles_out)
 {
-	uint8_t key[96];
+	uint8_t key[104];
 	memset(key, 0, sizeof key);
 	memcpy(key, m, 72);
 	memcpy(key + 72, &height, 4);
@@ -183,10 +194,13 @@ int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, fl
 	memcpy(key + 84, &offy, 4);
 	memcpy(key + 88, &wf, 4);
 	memcpy(key + 92, &hf, 4);
+	memcpy(key + 96, &wq, 4);
+	memcpy(key + 100, &hq, 4);
 	for (LutEntry& e : ctx->luts)
 		if (memcmp(e.key, key, sizeof key) == 0) {
 			e.stamp = ++ctx->lut_clock;
 			*out = e.d;
+			if (tiles_out) *tiles_out = e.tiles;
 			return VP_OK;
 		}
 	LutEntry* slot = nullptr;
@@ -199,33 +213,43 @@ int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, fl
 			if (e.stamp < slot->stamp)
 				slot = &e;
 		/* the evicted table may still be read by kernels in flight */
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		CK(ctx, cudaFree(slot->d));
+		CK(ctx, cudaDeviceSynchronize());
+		cudaFree(slot->d);
+		cudaFree(slot->tiles);
 		slot->d = nullptr;
+		slot->tiles = nullptr;
+		memset(slot->key, 0xff, sizeof slot->key);
+	}
+	const int tiles_x = cdiv(wf, FT_W), tiles_y = cdiv(hf, FT_H);
+	cudaError_t e = cudaMalloc(&slot->d, sizeof(float2) * (size_t)wf * hf);
+	if (e == cudaSuccess)
+		e = cudaMalloc(&slot->tiles, sizeof(TileEntry) * (size_t)tiles_x * tiles_y);
+	if (e != cudaSuccess) {
+		cudaFree(slot->d);
+		slot->d = nullptr;
+		slot->tiles = nullptr;
+		memset(slot->key, 0xff, sizeof slot->key);
+		return fail(ctx, VP_ERR_NOMEM, "coordinate table allocation failed: %s", cudaGetErrorString(e));
 	}
 	memcpy(slot->key, key, sizeof key);
 	slot->stamp = ++ctx->lut_clock;
-	cudaError_t e = cudaMalloc(&slot->d, sizeof(float2) * (size_t)wf * hf);
-	if (e != cudaSuccess) {
-		memset(slot->key, 0xff, sizeof slot->key);
-		slot->d = nullptr;
-		return fail(ctx, VP_ERR_NOMEM, "coordinate table allocation failed: %s", cudaGetErrorString(e));
-	}
 	{
-		Stage st(ctx, "coord_table");
+		Stage st(ctx, "coord_table", 2);
 		dim3 b(32, 8), g(cdiv(wf, 32), cdiv(hf, 8));
 		k_coord_table<<<g, b, 0, ctx->stream>>>(slot->d, *m, height, scale, offx, offy, wf, hf);
+		k_tile_table<<<dim3(tiles_x, tiles_y), 256, 0, ctx->stream>>>(slot->d, slot->tiles, wf, hf, wq, hq);
 	}
 	*out = slot->d;
-	return check_launch(ctx, "k_coord_table");
+	if (tiles_out) *tiles_out = slot->tiles;
+	return check_launch(ctx, "k_coord_table/k_tile_table");
 }
 
 template <class Src>
-int launch_reproject(vp_ctx* ctx, const Src& src, size_t frame_stride, int fmt, int mode, const float2* lut, uint32_t* flat, int wq,
+int launch_reproject(vp_ctx* ctx, cudaStream_t stream, const Src& src, size_t frame_stride, int fmt, int mode, const float2* lut, uint32_t* flat, int wq,
                      int hq, int nf, int n_frames)
 {
 	const dim3 g(cdiv(nf, 256), n_frames);
-#define VP_CALL k_reproject<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, frame_stride, lut, flat, wq, hq, nf)
+#define VP_CALL k_reproject<FMTC, MODE, Src><<<g, 256, 0, stream>>>(src, frame_stride, lut, flat, wq, hq, nf)
 	if (fmt == VP_FMT_RGGB8) { VP_DISPATCH_MODE(FMT_RGGB, mode, VP_CALL) }
 	else if (fmt == VP_FMT_GRBG8) { VP_DISPATCH_MODE(FMT_GRBG, mode, VP_CALL) }
 	else { VP_DISPATCH_MODE(FMT_BGR, mode, VP_CALL) }
@@ -257,16 +281,16 @@ int launch_quad2rgba(vp_ctx* ctx, const Src& src, int fmt, int mode, uint32_t* o
 	return check_launch(ctx, "k_quad2rgba");
 }
 
-int launch_colscan(vp_ctx* ctx, const int32_t* rowsum, float* sat, int wf, int hf, int n_frames, int* flag)
+int launch_colscan(vp_ctx* ctx, cudaStream_t stream, const int32_t* rowsum, float* sat, int wf, int hf, int n_frames, int* flag)
 {
 	const int rpw = cdiv(hf, 32);
 	const dim3 g(cdiv(wf, 32), n_frames);
 	if (rpw <= 16)
-		k_colscan<16><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+		k_colscan<16><<<g, 1024, 0, stream>>>(rowsum, sat, wf, hf, rpw, flag);
 	else if (rpw <= 32)
-		k_colscan<32><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+		k_colscan<32><<<g, 1024, 0, stream>>>(rowsum, sat, wf, hf, rpw, flag);
 	else if (rpw <= 48)
-		k_colscan<48><<<g, 1024, 0, ctx->stream>>>(rowsum, sat, wf, hf, rpw, flag);
+		k_colscan<48><<<g, 1024, 0, stream>>>(rowsum, sat, wf, hf, rpw, flag);
 	else
 		return fail(ctx, VP_ERR_UNSUPPORTED, "flat image height %d exceeds 1536 rows", hf);
 	return check_launch(ctx, "k_colscan");
@@ -275,17 +299,29 @@ int launch_colscan(vp_ctx* ctx, const int32_t* rowsum, float* sat, int wf, int h
 /* blobList.cl:79 can only reject when minScore > 0 or circularities may be negative */
 int need_score(float thr, float min_score) { return !(min_score <= 0.0f && thr >= 0.0f); }
 
-int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames)
+int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames, size_t mask_words)
 {
-	if (group_px > ctx->scratch_px) {
+	if (mask_words > ctx->mask_words_cap) {
 		CK(ctx, cudaStreamSynchronize(ctx->stream));
-		cudaFree(ctx->rowsum);
-		cudaFree(ctx->sat);
-		ctx->rowsum = nullptr;
-		ctx->sat = nullptr;
+		cudaFree(ctx->masks);
+		ctx->masks = nullptr;
+		ctx->mask_words_cap = 0;
+		CK(ctx, cudaMalloc(&ctx->masks, mask_words * 4));
+		ctx->mask_words_cap = mask_words;
+	}
+	if (group_px > ctx->scratch_px) {
+		CK(ctx, cudaDeviceSynchronize());
+		for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+			cudaFree(ctx->rowsum[l]);
+			cudaFree(ctx->sat[l]);
+			ctx->rowsum[l] = nullptr;
+			ctx->sat[l] = nullptr;
+		}
 		ctx->scratch_px = 0;
-		CK(ctx, cudaMalloc(&ctx->rowsum, group_px * 4));
-		CK(ctx, cudaMalloc(&ctx->sat, group_px * 4));
+		for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+			CK(ctx, cudaMalloc(&ctx->rowsum[l], group_px * 4));
+			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4));
+		}
 		ctx->scratch_px = group_px;
 	}
 	if (rows > ctx->rows_cap || frames > ctx->frames_cap) {
@@ -323,18 +359,25 @@ int validate_params(vp_ctx* ctx, const vp_params* p)
 
 size_t raw_frame_bytes(const vp_params* p) { return (size_t)p->wq * p->hq * (size_t)vp_format_pixel_size(p->fmt); }
 
-/* blob list of `n` frames: prepare (whole call) + count + emit */
+int launch_peaks_emit(vp_ctx* ctx, cudaStream_t stream, const uint32_t* flat, const float* circ, int w, int h, int n, int radius, int max_matches,
+                      const int32_t* first_slot, const int32_t* rowcount, const uint32_t* masks, uint8_t* matches, size_t match_stride)
+{
+	k_peaks_emit<<<dim3(cdiv(h, 8), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks, cdiv(w, 32), matches,
+	                                                           match_stride);
+	return check_launch(ctx, "k_peaks_emit");
+}
+
+/* blob list of `n` frames from materialised images (stage API): count + emit */
 int launch_blob_list(vp_ctx* ctx, const uint32_t* flat, const float* circ, int w, int h, int n, float thr, float min_score, int radius,
-                     int max_matches, int32_t* counter, int32_t* first_slot, int32_t* rowcount, uint8_t* matches, size_t match_stride)
+                     int max_matches, int32_t* counter, int32_t* first_slot, int32_t* rowcount, uint32_t* masks, uint8_t* matches,
+                     size_t match_stride)
 {
 	const int ns = need_score(thr, min_score);
-	k_peaks_count<<<dim3(cdiv(w, 256), h, n), 256, 0, ctx->stream>>>(flat, circ, w, h, thr, min_score, radius, ns, counter, rowcount);
+	k_peaks_count<<<dim3(cdiv(w, 256), h, n), 256, 0, ctx->stream>>>(flat, circ, w, h, thr, min_score, radius, ns, counter, rowcount, masks, cdiv(w, 32));
 	int rc = check_launch(ctx, "k_peaks_count");
 	if (rc)
 		return rc;
-	k_peaks_emit<<<dim3(cdiv(h, 8), n), 256, 0, ctx->stream>>>(flat, circ, w, h, thr, min_score, radius, ns, max_matches, first_slot, rowcount,
-	                                                           matches, match_stride);
-	return check_launch(ctx, "k_peaks_emit");
+	return launch_peaks_emit(ctx, ctx->stream, flat, circ, w, h, n, radius, max_matches, first_slot, rowcount, masks, matches, match_stride);
 }
 
 /* single-launch fallback: recompute the SAT of flagged frames in the reference's sequential order */
@@ -372,15 +415,20 @@ __global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad
 	}
 }
 
-int choose_group(vp_ctx* ctx, size_t nf, int n_frames)
+int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 {
 	if (ctx->group > 0)
 		return ctx->group < n_frames ? ctx->group : n_frames;
-	/* keep raw + flat + grad + rowsum + sat + circ of one group (~24 B/px) well inside the 126 MB L2 */
-	size_t g = (size_t)(72u << 20) / (24 * nf);
+	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over
+	 * one or two frames are launch- and tail-bound.  Groups of ~8 frames (10 Mpx) keep every kernel several waves long while
+	 * `lanes` groups in flight on separate streams let the issue-bound reprojection of one group overlap the bandwidth-bound
+	 * scans of another. */
+	size_t g = (size_t)10 * 1024 * 1024 / nf;
 	if (g < 1) g = 1;
-	if (g > 8) g = 8;
-	return (int)g < n_frames ? (int)g : n_frames;
+	if (g > 64) g = 64;
+	const size_t per_lane = ((size_t)n_frames + lanes - 1) / lanes;
+	if (g > per_lane) g = per_lane;
+	return (int)g;
 }
 
 } // namespace
@@ -422,6 +470,8 @@ const char* vp_last_error(const vp_ctx* ctx)
 	return t_last_error.c_str();
 }
 
+void vp_ctx_destroy(vp_ctx* c);
+
 int vp_ctx_create(int device, vp_ctx** out)
 {
 	if (!out)
@@ -447,6 +497,17 @@ int vp_ctx_create(int device, vp_ctx** out)
 		delete c;
 		return fail(nullptr, VP_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
 	}
+	c->lane_stream[0] = c->stream;
+	bool ok = cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) == cudaSuccess;
+	for (int l = 0; l < vp_ctx::MAX_LANES && ok; l++) {
+		if (l > 0)
+			ok = ok && cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess;
+		ok = ok && cudaEventCreateWithFlags(&c->lane_done[l], cudaEventDisableTiming) == cudaSuccess;
+	}
+	if (!ok) {
+		vp_ctx_destroy(c);
+		return fail(nullptr, VP_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+	}
 	*out = c;
 	return VP_OK;
 }
@@ -471,13 +532,23 @@ void vp_ctx_destroy(vp_ctx* c)
 	cudaStreamSynchronize(c->stream);
 	cudaStreamSynchronize(c->copy_in);
 	cudaStreamSynchronize(c->copy_out);
-	for (LutEntry& e : c->luts)
+	for (LutEntry& e : c->luts) {
 		cudaFree(e.d);
+		cudaFree(e.tiles);
+	}
 	for (ProfEntry& p : c->prof) {
 		cudaEventDestroy(p.start);
 		cudaEventDestroy(p.stop);
 	}
-	cudaFree(c->rowsum); cudaFree(c->sat); cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
+	cudaFree(c->masks);
+	for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+		cudaFree(c->rowsum[l]);
+		cudaFree(c->sat[l]);
+		if (l > 0 && c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
+		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
+	}
+	if (c->fork) cudaEventDestroy(c->fork);
+	cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
 	if (c->flag_host) cudaFreeHost(c->flag_host);
 	free_slots(c);
 	cudaStreamDestroy(c->stream);
@@ -501,6 +572,20 @@ int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group) /* tuning knob used by t
 {
 	REQUIRE(ctx, ctx && frames_per_group >= 0, "bad argument");
 	ctx->group = frames_per_group;
+	return VP_OK;
+}
+
+int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memory staged vs direct-gather reprojection */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->staged_reproject = on != 0;
+	return VP_OK;
+}
+
+int vp_ctx_set_lanes(vp_ctx* ctx, int lanes) /* concurrent streams the groups of one batch are spread over */
+{
+	REQUIRE(ctx, ctx && lanes >= 1 && lanes <= vp_ctx::MAX_LANES, "lanes must be in [1,%d]", vp_ctx::MAX_LANES);
+	ctx->lanes = lanes;
 	return VP_OK;
 }
 
@@ -753,10 +838,10 @@ int vp_resampling(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* flat, const
 		return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
 	const float2* lut;
-	rc = get_lut(ctx, model, height, scale, offx, offy, flat->w, flat->h, &lut);
+	rc = get_lut(ctx, model, height, scale, offx, offy, flat->w, flat->h, wq, hq, &lut, nullptr);
 	if (rc) return rc;
 	Stage st(ctx, "resampling");
-	return launch_reproject(ctx, planes_of(ch, fmt), 0, fmt, mode, lut, (uint32_t*)flat->buf->d, wq, hq, flat->w * flat->h, 1);
+	return launch_reproject(ctx, ctx->stream, planes_of(ch, fmt), 0, fmt, mode, lut, (uint32_t*)flat->buf->d, wq, hq, flat->w * flat->h, 1);
 }
 
 int vp_gradient_dot(vp_ctx* ctx, const vp_img* in, vp_img* out, int offset)
@@ -807,14 +892,14 @@ int vp_blob_list(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_buf* ma
 	REQUIRE(ctx, radius >= 0 && max_matches >= 0 && matches->size >= (size_t)max_matches * 22, "matches buffer smaller than max_matches records");
 	if (rgba->w == 0 || rgba->h == 0) return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
-	int rc = ensure_scratch(ctx, 0, rgba->h, 1);
+	int rc = ensure_scratch(ctx, 0, rgba->h, 1, (size_t)rgba->h * cdiv(rgba->w, 32));
 	if (rc) return rc;
 	Stage st(ctx, "blobList", 3);
 	k_peaks_prepare<<<cdiv(rgba->h, 256), 256, 0, ctx->stream>>>((int32_t*)counter->d, ctx->first_slot, ctx->rowcount, rgba->h, 1, 0, nullptr);
 	rc = check_launch(ctx, "k_peaks_prepare");
 	if (rc) return rc;
 	return launch_blob_list(ctx, (const uint32_t*)rgba->buf->d, (const float*)circ->buf->d, rgba->w, rgba->h, 1, thr, min_score, radius, max_matches,
-	                        (int32_t*)counter->d, ctx->first_slot, ctx->rowcount, (uint8_t*)matches->d, 0);
+	                        (int32_t*)counter->d, ctx->first_slot, ctx->rowcount, ctx->masks, (uint8_t*)matches->d, 0);
 }
 
 static int check_nv12(vp_ctx* ctx, int w, int h, const vp_buf* nv12)
@@ -963,65 +1048,113 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	const int wf = p->wf, hf = p->hf;
 	const size_t nf = (size_t)wf * hf;
 	const size_t raw_bytes = raw_frame_bytes(p);
-	const int G = choose_group(ctx, nf, n_frames);
-	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames);
+	const int lanes_max = ctx->profiling ? 1 : ctx->lanes; /* per-stage event timing is only meaningful on one stream */
+	const int G = choose_group(ctx, nf, n_frames, lanes_max);
+	const int n_groups = cdiv(n_frames, G);
+	const int lanes = n_groups < lanes_max ? n_groups : lanes_max;
+	const int wpr = cdiv(wf, 32);
+	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
+	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
 	const float2* lut;
-	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, &lut);
+	const TileEntry* tiles;
+	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, p->wq, p->hq, &lut, &tiles);
 	if (rc) return rc;
+	const bool staged = ctx->staged_reproject && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
+	const int ns = need_score(p->circ_threshold, p->min_score);
 
-	cudaStream_t s = ctx->stream;
 	{
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
-		k_peaks_prepare<<<cdiv(n, 256), 256, 0, s>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag);
+		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
-	for (int f0 = 0; f0 < n_frames; f0 += G) {
+	if (lanes > 1) { /* fork: the other lanes start after everything already enqueued on the context stream */
+		CK(ctx, cudaEventRecord(ctx->fork, ctx->stream));
+		for (int l = 1; l < lanes; l++)
+			CK(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork, 0));
+	}
+	for (int gi = 0; gi < n_groups; gi++) {
+		const int f0 = gi * G;
 		const int g = n_frames - f0 < G ? n_frames - f0 : G;
+		const int lane = gi % lanes;
+		cudaStream_t s = ctx->lane_stream[lane];
+		int32_t* rowsum = ctx->rowsum[lane];
+		float* sat = ctx->sat[lane];
 		uint32_t* flat = (uint32_t*)d_flat + (size_t)f0 * nf;
 		float* grad = d_grad + (size_t)f0 * nf;
 		float* circ = d_circ + (size_t)f0 * nf;
 		const uint8_t* raw = d_raw + (size_t)f0 * raw_bytes;
+		int* flag = ctx->flag + f0;
+		int32_t* counter = d_counter + 3 * (size_t)f0;
+		int32_t* rowcount = ctx->rowcount + (size_t)f0 * hf;
+		uint32_t* masks = ctx->masks + (size_t)f0 * hf * wpr;
 		{
-			Stage st(ctx, "reproject");
-			if (p->fmt == VP_FMT_BGR8) {
+			Stage st(ctx, "reproject", 1, s);
+			if (staged) {
+				const int tiles_x = cdiv(wf, FT_W);
+				const dim3 grid(tiles_x * cdiv(hf, FT_H), g);
+				if (p->fmt == VP_FMT_RGGB8)
+					k_reproject_staged<FMT_RGGB><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, tiles_x);
+				else
+					k_reproject_staged<FMT_GRBG><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, tiles_x);
+				rc = check_launch(ctx, "k_reproject_staged");
+			} else if (p->fmt == VP_FMT_BGR8) {
 				SrcBGR src{ raw, p->wq };
-				rc = launch_reproject(ctx, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
+				rc = launch_reproject(ctx, s, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
 			} else {
 				SrcBayer src{ raw, 2 * p->wq };
-				rc = launch_reproject(ctx, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
+				rc = launch_reproject(ctx, s, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
 			}
 			if (rc) return rc;
 		}
 		{
-			Stage st(ctx, "grad_rowscan");
-			k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, ctx->rowsum, wf, hf, p->grad_offset, ctx->flag + f0);
+			Stage st(ctx, "grad_rowscan", 1, s);
+			k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
 			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
 		}
 		{
-			Stage st(ctx, "colscan");
-			if ((rc = launch_colscan(ctx, ctx->rowsum, ctx->sat, wf, hf, g, ctx->flag + f0))) return rc;
+			Stage st(ctx, "colscan", 1, s);
+			if ((rc = launch_colscan(ctx, s, rowsum, sat, wf, hf, g, flag))) return rc;
 		}
 		{
-			Stage st(ctx, "sat_fix");
-			k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)ctx->rowsum, ctx->sat, wf, hf, ctx->flag + f0);
+			Stage st(ctx, "sat_fix", 1, s);
+			k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag);
 			if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
 		}
-		{
-			Stage st(ctx, "circle");
-			k_circle<<<dim3(cdiv(wf, 64), cdiv(hf, 4), g), 256, 0, s>>>(ctx->sat, circ, wf, hf, p->circle_radius);
+		if (fused_circ) {
+			Stage st(ctx, "circ_peaks", 1, s);
+			const dim3 grid(cdiv(wf, CT_W), cdiv(hf, CT_H), g);
+#define VP_CP(RR)                                                                                                              \
+	case RR:                                                                                                                   \
+		k_circ_peaks<RR><<<grid, 256, 0, s>>>(sat, circ, flat, wf, hf, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
+		                                      rowcount, masks, wpr);                                                           \
+		break;
+			switch (p->circle_radius) {
+				VP_CP(1) VP_CP(2) VP_CP(3) VP_CP(4) VP_CP(5) VP_CP(6) VP_CP(7) VP_CP(8) VP_CP(9) VP_CP(10) VP_CP(11) VP_CP(12)
+			}
+#undef VP_CP
+			if ((rc = check_launch(ctx, "k_circ_peaks"))) return rc;
+		} else { /* radius outside the specialised range: unfused circle + count */
+			Stage st(ctx, "circle+count", 2, s);
+			k_circle<<<dim3(cdiv(wf, 64), cdiv(hf, 4), g), 256, 0, s>>>(sat, circ, wf, hf, p->circle_radius);
 			if ((rc = check_launch(ctx, "k_circle"))) return rc;
+			k_peaks_count<<<dim3(cdiv(wf, 256), hf, g), 256, 0, s>>>(flat, circ, wf, hf, p->circ_threshold, p->min_score, p->blob_radius, ns, counter, rowcount,
+			                                                        masks, wpr);
+			if ((rc = check_launch(ctx, "k_peaks_count"))) return rc;
 		}
 		{
-			Stage st(ctx, "blob_list", 2);
-			rc = launch_blob_list(ctx, flat, circ, wf, hf, g, p->circ_threshold, p->min_score, p->blob_radius, p->max_blobs, d_counter + 3 * (size_t)f0,
-			                      ctx->first_slot + f0, ctx->rowcount + (size_t)f0 * hf, (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22,
-			                      (size_t)p->max_blobs * 22);
+			Stage st(ctx, "peaks_emit", 1, s);
+			rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
+			                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22);
 			if (rc) return rc;
 		}
 	}
-	CK(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, s));
+	for (int l = 1; l < lanes; l++) { /* join */
+		CK(ctx, cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_done[l], 0));
+	}
+	CK(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	ctx->last_fallbacks = -n_frames; /* negative: flag_host holds n flags not summed yet */
 	return VP_OK;
 }

@@ -115,6 +115,8 @@ def load() -> C.CDLL:
         "vp_ctx_sync": (C.c_int, [vp]),
         "vp_ctx_stream": (vp, [vp]),
         "vp_ctx_set_group": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_lanes": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
         "vp_profiling_enable": (C.c_int, [vp, C.c_int]),
         "vp_profiling_count": (C.c_int, [vp]),
@@ -330,6 +332,12 @@ class Context:
 
     def set_group(self, n: int):
         self._ck(self.lib.vp_ctx_set_group(self.h, n))
+
+    def set_staged_reproject(self, on: bool):
+        self._ck(self.lib.vp_ctx_set_staged_reproject(self.h, int(on)))
+
+    def set_lanes(self, n: int):
+        self._ck(self.lib.vp_ctx_set_lanes(self.h, n))
 
     # ---- profiling (OpenCL::printRuntimes, opencl.cpp:94-101) -----------------------------------
     def profiling(self, on: bool):
