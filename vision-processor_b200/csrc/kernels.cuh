@@ -378,39 +378,86 @@ __global__ void __launch_bounds__(256) k_tile_table(const float2* __restrict__ l
 	}
 }
 
-/* one bilinear sample from a staged plane: taps are immediate offsets from one address */
-__device__ __forceinline__ uint32_t blend_rte_staged(const float* __restrict__ t, float xa, float xoma, float ya, float yoma)
+/* Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, new on sm_100): two IEEE round-to-nearest operations per issue
+ * slot.  The staged kernel is issue-bound, so the two x axes, the two y axes and two samples at a time are evaluated
+ * as pairs.  a - b is written fma2(b, -1, a): the product is exact, so the single rounding equals the subtraction's. */
+/* Explicit PTX.  CAUTION: ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 regardless of -fmad
+ * (also through an fma against -0) -- seen in SASS, and in 0.1 % of the pixels as a 1-LSB difference.  A packed product
+ * must therefore never feed a packed add: products are packed, their accumulation is scalar (FMUL2 -> FADD is left alone). */
+__device__ __forceinline__ unsigned long long f2_bits(float2 v)
 {
-	const float w00 = __fmul_rn(xoma, yoma), w10 = __fmul_rn(xa, yoma), w01 = __fmul_rn(xoma, ya), w11 = __fmul_rn(xa, ya);
-	const float val = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w00, t[0]), __fmul_rn(w10, t[1])), __fmul_rn(w01, t[TQ_W])), __fmul_rn(w11, t[TQ_W + 1]));
-	return min(__float_as_uint(__fadd_rn(val, 8388608.0f)) - 0x4B000000u, 255u);
+	unsigned long long r;
+	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+	return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long r)
+{
+	float2 v;
+	asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+	return v;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+	unsigned long long r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+	return bits_f2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+	unsigned long long r;
+	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+	return bits_f2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(b)), "l"(f2_bits(make_float2(-1.0f, -1.0f))), "l"(f2_bits(a)));
+	return bits_f2(r);
 }
 
-/* tile-relative axis: index into the staged planes (no clamp: the edge texels are replicated in the tile) */
-__device__ __forceinline__ void axis_staged(float u, int origin_magic, int& ii, float& a, float& oma)
+/* two tile-relative axes at once (u.x, u.y share the plane dimension): indices into the staged planes, no clamp
+ * (edge texels are replicated in the tile); bit-identical to axis_setup */
+__device__ __forceinline__ void axis_staged2(float2 u, int origin_magic, int& i0, int& i1, float2& a, float2& oma)
 {
 	constexpr float M = 12582912.0f;
-	const float fu = __fsub_rn(u, 0.5f);
-	const float t = __fadd_rn(fu, M);
-	const float r = __fsub_rn(t, M);
-	const bool dec = r > fu;
-	const float fi = dec ? __fsub_rn(r, 1.0f) : r;
-	ii = __float_as_int(t) - origin_magic - (dec ? 1 : 0);
-	a = __fsub_rn(fu, fi);
-	oma = __fsub_rn(1.0f, a);
+	const float2 fu = add2(u, make_float2(-0.5f, -0.5f));
+	const float2 t = add2(fu, make_float2(M, M));
+	const float2 r = add2(t, make_float2(-M, -M)); /* rint(fu) */
+	const bool d0 = r.x > fu.x, d1 = r.y > fu.y;
+	const float2 fi = add2(r, make_float2(d0 ? -1.0f : 0.0f, d1 ? -1.0f : 0.0f)); /* floor(fu) */
+	i0 = __float_as_int(t.x) - origin_magic - (d0 ? 1 : 0);
+	i1 = __float_as_int(t.y) - origin_magic - (d1 ? 1 : 0);
+	a = sub2(fu, fi);
+	oma = sub2(make_float2(1.0f, 1.0f), a);
+}
+
+/* two bilinear samples at once from staged planes: sample k taps tk[0], tk[1], tk[TQ_W], tk[TQ_W+1] */
+__device__ __forceinline__ void blend_rte_staged2(const float* __restrict__ t0, const float* __restrict__ t1, float2 xa, float2 xoma, float2 ya, float2 yoma,
+                                                  uint32_t& v0, uint32_t& v1)
+{
+	const float2 w00 = mul2(xoma, yoma), w10 = mul2(xa, yoma), w01 = mul2(xoma, ya), w11 = mul2(xa, ya);
+	const float2 p00 = mul2(w00, make_float2(t0[0], t1[0]));
+	const float2 p10 = mul2(w10, make_float2(t0[1], t1[1]));
+	const float2 p01 = mul2(w01, make_float2(t0[TQ_W], t1[TQ_W]));
+	const float2 p11 = mul2(w11, make_float2(t0[TQ_W + 1], t1[TQ_W + 1]));
+	float2 val; /* scalar accumulation, see the note at add2/mul2 */
+	val.x = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p10.x), p01.x), p11.x);
+	val.y = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p10.y), p01.y), p11.y);
+	const float2 rn = add2(val, make_float2(8388608.0f, 8388608.0f)); /* RNE to integer in the mantissa */
+	v0 = min(__float_as_uint(rn.x) - 0x4B000000u, 255u);
+	v1 = min(__float_as_uint(rn.y) - 0x4B000000u, 255u);
 }
 
 template <int FMT>
 __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
                                                            const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq, int wf,
-                                                           int hf, int tiles_x)
+                                                           int hf)
 {
 	__shared__ __align__(16) float T[4 * TQ_H * TQ_W];
-	const int tile = blockIdx.x;
-	const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-	const uint8_t* raw = raw0 + (size_t)blockIdx.y * frame_stride;
-	uint32_t* out = flat + (size_t)blockIdx.y * wf * hf;
-	const TileEntry e = table[tile];
+	const int tx = blockIdx.x, ty = blockIdx.y;
+	const uint8_t* raw = raw0 + (size_t)blockIdx.z * frame_stride;
+	uint32_t* out = flat + (size_t)blockIdx.z * wf * hf;
+	const TileEntry e = table[ty * gridDim.x + tx];
 	const int tid = threadIdx.x;
 	const int lx = tid & 63, ly = tid >> 6;
 	const int gx = tx * FT_W + lx;
@@ -420,7 +467,7 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 		for (int k = 0; k < 4; k++) {
 			const int gy = ty * FT_H + ly + 4 * k;
 			if (gx < wf && gy < hf) {
-				const float2 pos = __ldg(lut + (size_t)gy * wf + gx);
+				const float2 pos = __ldg(lut + (gy * wf + gx));
 				uint32_t v;
 				if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
 					v = reproject_bayer_rte_fast<FMT>(raw, wq, hq, pos.x, pos.y);
@@ -430,21 +477,21 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 					demosaic<FMT, MODE_RTE>(s, wq, hq, pos.x, pos.y, r, g, b);
 					v = drgb(r, g, b);
 				}
-				out[(size_t)gy * wf + gx] = v;
+				out[gy * wf + gx] = v;
 			}
 		}
 		return;
 	}
 
-	const size_t row_bytes = 2 * (size_t)wq;
+	const int row_bytes = 2 * wq;
 	if (e.flags & 2) {
 		/* 16-byte vectors: raw row 2*jj + s holds planes (2s, 2s+1) of quad row jj interleaved */
 		constexpr int NV = TQ_W / 8;
 		const int total = NV * 2 * e.height;
-		const uint8_t* src = raw + (size_t)(2 * e.jb) * row_bytes + 2 * (size_t)e.ib;
+		const uint8_t* src = raw + (2 * e.jb * row_bytes + 2 * e.ib);
 		for (int v = tid; v < total; v += 256) {
 			const int rr = v / NV, cv = v - rr * NV;
-			const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (size_t)rr * row_bytes) + cv);
+			const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (rr * row_bytes + cv * 16)));
 			float* d0 = T + ((rr & 1) * 2 * TQ_H + (rr >> 1)) * TQ_W + cv * 8; /* plane 2s */
 			float* d1 = d0 + TQ_H * TQ_W;                                     /* plane 2s+1 */
 			const uint32_t wds[4] = { q.x, q.y, q.z, q.w };
@@ -468,7 +515,7 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 			const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
 			const int jj = rc >> 2, c = rc & 3;
 			const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
-			const uint32_t b = __ldg(raw + (size_t)(2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1));
+			const uint32_t b = __ldg(raw + ((2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1)));
 			T[(c * TQ_H + jj) * TQ_W + ii] = u8_to_float(b);
 		}
 	}
@@ -479,21 +526,18 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 	for (int k = 0; k < 4; k++) {
 		const int gy = ty * FT_H + ly + 4 * k;
 		if (gx < wf && gy < hf) {
-			const float2 pos = __ldg(lut + (size_t)gy * wf + gx);
+			const float2 pos = __ldg(lut + (gy * wf + gx));
 			int ixp, ixn, iyp, iyn;
-			float axp, oxp, axn, oxn, ayp, oyp, ayn, oyn;
-			axis_staged(__fadd_rn(pos.x, 0.25f), xmagic, ixp, axp, oxp);
-			axis_staged(__fsub_rn(pos.x, 0.25f), xmagic, ixn, axn, oxn);
-			axis_staged(__fadd_rn(pos.y, 0.25f), ymagic, iyp, ayp, oyp);
-			axis_staged(__fsub_rn(pos.y, 0.25f), ymagic, iyn, ayn, oyn);
+			float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
+			axis_staged2(add2(make_float2(pos.x, pos.x), make_float2(0.25f, -0.25f)), xmagic, ixp, ixn, ax, ox);
+			axis_staged2(add2(make_float2(pos.y, pos.y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
 			const float* rowp = T + iyp * TQ_W;
 			const float* rown = T + iyn * TQ_W;
 			/* plane 0 at (+,+), 1 at (-,+), 2 at (+,-), 3 at (-,-)  (resampling.cl:65-80) */
-			const uint32_t v0 = blend_rte_staged(rowp + ixp, axp, oxp, ayp, oyp);
-			const uint32_t v1 = blend_rte_staged(rowp + TQ_H * TQ_W + ixn, axn, oxn, ayp, oyp);
-			const uint32_t v2 = blend_rte_staged(rown + 2 * TQ_H * TQ_W + ixp, axp, oxp, ayn, oyn);
-			const uint32_t v3 = blend_rte_staged(rown + 3 * TQ_H * TQ_W + ixn, axn, oxn, ayn, oyn);
-			out[(size_t)gy * wf + gx] = FMT == FMT_RGGB ? drgb(v0, v1 / 2 + v2 / 2, v3) : drgb(v1, v0 / 2 + v3 / 2, v2);
+			uint32_t v0, v1, v2, v3;
+			blend_rte_staged2(rowp + ixp, rowp + TQ_H * TQ_W + ixn, ax, ox, make_float2(ay.x, ay.x), make_float2(oy.x, oy.x), v0, v1);
+			blend_rte_staged2(rown + 2 * TQ_H * TQ_W + ixp, rown + 3 * TQ_H * TQ_W + ixn, ax, ox, make_float2(ay.y, ay.y), make_float2(oy.y, oy.y), v2, v3);
+			out[gy * wf + gx] = FMT == FMT_RGGB ? drgb(v0, v1 / 2 + v2 / 2, v3) : drgb(v1, v0 / 2 + v3 / 2, v2);
 		}
 	}
 }
@@ -660,13 +704,15 @@ __global__ void __launch_bounds__(1024) k_colscan(const int32_t* __restrict__ ro
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int x = blockIdx.x * 32 + lane;
 	const size_t fbase = (size_t)blockIdx.y * wf * hf;
+	const int32_t* src = rowsum + fbase;
+	float* dst = sat + fbase;
 	const int y0 = warp * rpw;
 	int v[RPW];
 	int sum = 0;
 #pragma unroll
 	for (int k = 0; k < RPW; k++) {
 		const int y = y0 + k;
-		v[k] = (k < rpw && y < hf && x < wf) ? __ldg(rowsum + fbase + (size_t)y * wf + x) : 0;
+		v[k] = (k < rpw && y < hf && x < wf) ? __ldg(src + (y * wf + x)) : 0;
 	}
 #pragma unroll
 	for (int k = 0; k < RPW; k++) {
@@ -685,7 +731,7 @@ __global__ void __launch_bounds__(1024) k_colscan(const int32_t* __restrict__ ro
 		if (k < rpw && y < hf && x < wf) {
 			const int s = v[k] + off;
 			bad |= abs(s) >= SAT_EXACT_LIMIT;
-			sat[fbase + (size_t)y * wf + x] = (float)s;
+			dst[y * wf + x] = (float)s;
 		}
 	}
 	if (bad)
@@ -851,17 +897,17 @@ __device__ __forceinline__ int peak_class(const uint32_t* __restrict__ img, cons
  * bit masks, counts blobs per row and accumulates counter[0..2]; pass B (k_peaks_emit) ranks the set bits in raster
  * order (first slot + blobs of earlier rows + blobs to the left) and writes the records with rank < max_matches. */
 
-/* publish one warp's classification of 32 consecutive pixels of row y (segment index seg) */
-__device__ __forceinline__ void publish_segment(int cls, int lane, bool seg_valid, int32_t* __restrict__ rowcount_f, uint32_t* __restrict__ masks_f,
+/* publish one warp's classification of 32 consecutive pixels of row y (segment index seg).  The mask words were
+ * zeroed by k_peaks_prepare, so only segments that hold a blob are written. */
+__device__ __forceinline__ void publish_segment(int cls, int lane, int32_t* __restrict__ rowcount_f, uint32_t* __restrict__ masks_f,
                                                 int wpr, int y, int seg, int& n_blob, int& n_score, int& n_peak)
 {
 	const unsigned m3 = __ballot_sync(0xffffffffu, cls == 3);
 	const unsigned m2 = __ballot_sync(0xffffffffu, cls == 2);
 	const unsigned m1 = __ballot_sync(0xffffffffu, cls == 1);
-	if (lane == 0 && seg_valid) {
-		masks_f[(size_t)y * wpr + seg] = m3;
-		if (m3)
-			atomicAdd(rowcount_f + y, __popc(m3));
+	if (lane == 0 && m3) {
+		masks_f[y * wpr + seg] = m3;
+		atomicAdd(rowcount_f + y, __popc(m3));
 	}
 	n_blob += __popc(m3);
 	n_score += __popc(m2);
@@ -895,7 +941,7 @@ __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict_
 		cls = peak_class(img + fbase, circ + fbase, w, h, x, y, thr, min_score, radius, need_score != 0, p);
 	}
 	int nb = 0, ns = 0, np = 0;
-	publish_segment(cls, threadIdx.x & 31, (x & ~31) < w, rowcount + (size_t)f * h, masks + (size_t)f * h * wpr, wpr, y, x >> 5, nb, ns, np);
+	publish_segment(cls, threadIdx.x & 31, rowcount + (size_t)f * h, masks + (size_t)f * h * wpr, wpr, y, x >> 5, nb, ns, np);
 	publish_counters(threadIdx.x & 31, counter + 3 * f, nb, ns, np);
 }
 
@@ -953,18 +999,18 @@ __global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sa
 			const int j0 = g * RPG;
 			float a[RPG + K], b[RPG + K];
 			if (inner) {
-				const float* p = satf + (size_t)(qy0 + j0) * w + (qx0 + i);
+				const float* p = satf + ((qy0 + j0) * w + (qx0 + i));
 #pragma unroll
 				for (int j = 0; j < RPG + K; j++) {
 					const bool ok = j0 + j < QH + K;
-					a[j] = ok ? __ldg(p + (size_t)j * w) : 0.f;
-					b[j] = ok ? __ldg(p + (size_t)j * w + K) : 0.f;
+					a[j] = ok ? __ldg(p + j * w) : 0.f;
+					b[j] = ok ? __ldg(p + j * w + K) : 0.f;
 				}
 			} else {
 				const int xa = clampi(qx0 + i, 0, w - 1), xb = clampi(qx0 + i + K, 0, w - 1);
 #pragma unroll
 				for (int j = 0; j < RPG + K; j++) {
-					const float* row = satf + (size_t)clampi(qy0 + j0 + j, 0, h - 1) * w;
+					const float* row = satf + clampi(qy0 + j0 + j, 0, h - 1) * w;
 					a[j] = __ldg(row + xa);
 					b[j] = __ldg(row + xb);
 				}
@@ -979,56 +1025,69 @@ __global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sa
 
 	constexpr float D = (float)(R * R);
 	constexpr float Y = 1.0f / D; /* correctly rounded reciprocal */
-	for (int idx = tid; idx < CW * CH; idx += 256) {
-		const int cj = idx / CW, ci = idx - cj * CW;
-		const int px = x0 - 1 + ci, py = y0 - 1 + cj;
-		int cx = px, cy = py;
-		bool fast = !flagged;
-		if (!inner) {
-			cx = clampi(px, 0, w - 1);
-			cy = clampi(py, 0, h - 1);
-			fast = fast && cx - R >= 0 && cx + R <= w - 1 && cy - R >= 0 && cy + R <= h - 1;
+	float* circf = circ_out + fbase;
+	/* walk the (CT_W+2) x (CT_H+2) ring tile with stride 256 without dividing: 256 = (256/CW)*CW + 256%CW */
+	int cj = tid / CW, ci = tid - cj * CW;
+#pragma unroll 3
+	for (int it = 0; it < (CW * CH + 255) / 256; it++) {
+		if (cj < CH) {
+			const int px = x0 - 1 + ci, py = y0 - 1 + cj;
+			float c;
+			if (inner && !flagged) {
+				/* Q index of image coordinate u is u - (x0-1-R): Q(px-R, .) sits at ci, Q(px+1, .) R+1 further */
+				const float* q = Q + (cj * QW + ci);
+				const float pp = q[(R + 1) * QW + (R + 1)];
+				const float nn = q[0];
+				const float pn = __fsub_rn(0.0f, q[R + 1]);        /* 0 - Q keeps +0 where the reference's last addition yields +0 */
+				const float np = __fsub_rn(0.0f, q[(R + 1) * QW]);
+				const float m = fminf(fminf(pp, nn), fminf(pn, np));
+				const float q0 = __fmul_rn(m, Y);
+				c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0); /* == m / D, satBlobCenter.cl:41 */
+			} else {
+				const int cx = clampi(px, 0, w - 1), cy = clampi(py, 0, h - 1);
+				if (!flagged && cx - R >= 0 && cx + R <= w - 1 && cy - R >= 0 && cy + R <= h - 1) {
+					const float* q = Q + ((cy - (y0 - 1)) * QW + (cx - (x0 - 1)));
+					const float m = fminf(fminf(q[(R + 1) * QW + (R + 1)], q[0]), fminf(__fsub_rn(0.0f, q[R + 1]), __fsub_rn(0.0f, q[(R + 1) * QW])));
+					const float q0 = __fmul_rn(m, Y);
+					c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0);
+				} else {
+					c = circle_px_generic(satf, w, h, cx, cy, R);
+				}
+			}
+			Cc[cj * CW + ci] = c;
+			if ((unsigned)(ci - 1) < (unsigned)CT_W && (unsigned)(cj - 1) < (unsigned)CT_H && px < w && py < h)
+				circf[py * w + px] = c;
 		}
-		float c;
-		if (fast) {
-			/* Q index of image coordinate u is u - (x0-1-R): Q(cx-R, .) sits at cx-(x0-1), Q(cx+1, .) R+1 further */
-			const float* q = Q + (cy - (y0 - 1)) * QW + (cx - (x0 - 1));
-			const float pp = q[(R + 1) * QW + (R + 1)];
-			const float nn = q[0];
-			const float pn = __fsub_rn(0.0f, q[R + 1]);        /* 0 - Q keeps +0 where the reference's last addition yields +0 */
-			const float np = __fsub_rn(0.0f, q[(R + 1) * QW]);
-			const float m = fminf(fminf(pp, nn), fminf(pn, np));
-			const float q0 = __fmul_rn(m, Y);
-			c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0); /* == m / D, satBlobCenter.cl:41 */
-		} else {
-			c = circle_px_generic(satf, w, h, cx, cy, R);
+		ci += 256 % CW;
+		cj += 256 / CW;
+		if (ci >= CW) {
+			ci -= CW;
+			cj++;
 		}
-		Cc[idx] = c;
-		if (ci >= 1 && ci <= CT_W && cj >= 1 && cj <= CT_H && px < w && py < h)
-			circ_out[fbase + (size_t)py * w + px] = c;
 	}
 	__syncthreads();
 
-	/* peak classification: warp -> 4 rows x 2 segments of 32 pixels */
+	/* peak classification: warp -> 4 rows x 2 segments of 32 pixels; almost every segment is entirely below the threshold */
 	int nb = 0, ns = 0, npk = 0;
-	int32_t* rc = rowcount + (size_t)f * h;
+	int32_t* rc = rowcount + f * h;
 	uint32_t* mk = masks + (size_t)f * h * wpr;
 #pragma unroll 1
 	for (int q = 0; q < 8; q++) {
 		const int ty = warp * 4 + (q >> 1), tx = (q & 1) * 32 + lane;
 		const int x = x0 + tx, y = y0 + ty;
+		const float* cc = Cc + (ty + 1) * CW + tx + 1;
+		const float c = cc[0];
+		const bool cand = x < w && y < h && !(c < thr); /* blobList.cl:39 */
+		if (!__any_sync(0xffffffffu, cand))
+			continue;
 		int cls = 0;
-		if (x < w && y < h) {
-			const float* cc = Cc + (ty + 1) * CW + tx + 1;
-			const float c = cc[0];
-			if (!(c < thr)) { /* blobList.cl:39 */
-				if (cc[-1] > c || cc[1] > c || cc[-CW] > c || cc[CW] > c) /* :47-55; the ring holds the clamped neighbours */
-					cls = 1;
-				else
-					cls = need_score ? classify_by_score(flat + fbase, w, h, x, y, radius, c, min_score) : 3; /* :79 */
-			}
+		if (cand) {
+			if (cc[-1] > c || cc[1] > c || cc[-CW] > c || cc[CW] > c) /* :47-55; the ring holds the clamped neighbours */
+				cls = 1;
+			else
+				cls = need_score ? classify_by_score(flat + fbase, w, h, x, y, radius, c, min_score) : 3; /* :79 */
 		}
-		publish_segment(cls, lane, y < h && x0 + (q & 1) * 32 < w, rc, mk, wpr, y < h ? y : 0, (x0 >> 5) + (q & 1), nb, ns, npk);
+		publish_segment(cls, lane, rc, mk, wpr, y, (x0 >> 5) + (q & 1), nb, ns, npk);
 	}
 	publish_counters(lane, counter + 3 * f, nb, ns, npk);
 }
@@ -1144,9 +1203,11 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 /* per-batch preparation of the compaction scratch: zero the row counts and the exactness flags; either zero the
  * counters (fused path, main.cpp:283-288) or remember counter[0] as the first output slot (stage API). */
 __global__ void k_peaks_prepare(int32_t* __restrict__ counter, int32_t* __restrict__ first_slot, int32_t* __restrict__ rowcount,
-                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag)
+                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag, uint32_t* __restrict__ masks, int n_mask_words)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int k = i; k < n_mask_words; k += gridDim.x * blockDim.x)
+		masks[k] = 0u;
 	if (i < n_rows_total)
 		rowcount[i] = 0;
 	if (i < n_frames) {

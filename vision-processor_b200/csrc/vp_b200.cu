@@ -895,7 +895,8 @@ int vp_blob_list(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_buf* ma
 	int rc = ensure_scratch(ctx, 0, rgba->h, 1, (size_t)rgba->h * cdiv(rgba->w, 32));
 	if (rc) return rc;
 	Stage st(ctx, "blobList", 3);
-	k_peaks_prepare<<<cdiv(rgba->h, 256), 256, 0, ctx->stream>>>((int32_t*)counter->d, ctx->first_slot, ctx->rowcount, rgba->h, 1, 0, nullptr);
+	k_peaks_prepare<<<cdiv(rgba->h, 256), 256, 0, ctx->stream>>>((int32_t*)counter->d, ctx->first_slot, ctx->rowcount, rgba->h, 1, 0, nullptr, ctx->masks,
+	                                                             rgba->h * cdiv(rgba->w, 32));
 	rc = check_launch(ctx, "k_peaks_prepare");
 	if (rc) return rc;
 	return launch_blob_list(ctx, (const uint32_t*)rgba->buf->d, (const float*)circ->buf->d, rgba->w, rgba->h, 1, thr, min_score, radius, max_matches,
@@ -1066,7 +1067,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	{
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
-		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag);
+		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
 	if (lanes > 1) { /* fork: the other lanes start after everything already enqueued on the context stream */
@@ -1092,12 +1093,11 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		{
 			Stage st(ctx, "reproject", 1, s);
 			if (staged) {
-				const int tiles_x = cdiv(wf, FT_W);
-				const dim3 grid(tiles_x * cdiv(hf, FT_H), g);
+				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), g);
 				if (p->fmt == VP_FMT_RGGB8)
-					k_reproject_staged<FMT_RGGB><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, tiles_x);
+					k_reproject_staged<FMT_RGGB><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf);
 				else
-					k_reproject_staged<FMT_GRBG><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, tiles_x);
+					k_reproject_staged<FMT_GRBG><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf);
 				rc = check_launch(ctx, "k_reproject_staged");
 			} else if (p->fmt == VP_FMT_BGR8) {
 				SrcBGR src{ raw, p->wq };
