@@ -218,6 +218,9 @@ VP_API int vp_ctx_set_lanes(vp_ctx* ctx, int lanes);
 /* A/B switch (default on): reprojection through the shared-memory staged kernel vs the direct-gather kernel; results
  * are bit-identical */
 VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
+/* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
+ * tiled kernel; results are bit-identical */
+VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 VP_API uint64_t vp_launch_count(const vp_ctx* ctx);

@@ -23,6 +23,7 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--group", type=int, default=0)
 ap.add_argument("--lanes", type=int, default=3)
 ap.add_argument("--direct", action="store_true", help="direct-gather reprojection instead of the staged kernel")
+ap.add_argument("--tiled-circ", action="store_true", help="shared-memory tiled circularity kernel instead of the streaming one")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--times", action="store_true", help="print CUDA-event time per step and per stage")
@@ -45,6 +46,7 @@ ctx = lib.Context(0)
 ctx.set_group(args.group)
 ctx.set_lanes(args.lanes)
 ctx.set_staged_reproject(not args.direct)
+ctx.set_stream_circ(not args.tiled_circ)
 
 
 def step():

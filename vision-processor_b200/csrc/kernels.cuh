@@ -33,6 +33,17 @@ constexpr int SAT_EXACT_LIMIT = 1 << 22;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+/* &base[idx] as ONE instruction (IMAD.WIDE.U32): nvcc otherwise expands pointer + 32-bit index into a 4-instruction
+ * 64-bit add/shift sequence and rematerialises the base, which matters in kernels that are issue-bound */
+template <class T>
+__device__ __forceinline__ T* elem_ptr(T* base, unsigned idx)
+{
+	static_assert(sizeof(T) == 4, "4-byte elements");
+	unsigned long long r;
+	asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
+	return reinterpret_cast<T*>(r);
+}
+
 /* float -> texel index: saturating, NaN -> 0 (fmaxf/fminf return the non-NaN operand) */
 __device__ __forceinline__ int sat_index(float f, int n)
 {
@@ -1088,6 +1099,140 @@ __global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sa
 				cls = need_score ? classify_by_score(flat + fbase, w, h, x, y, radius, c, min_score) : 3; /* :79 */
 		}
 		publish_segment(cls, lane, rc, mk, wpr, y, (x0 >> 5) + (q & 1), nb, ns, npk);
+	}
+	publish_counters(lane, counter + 3 * f, nb, ns, npk);
+}
+
+/* K3, register-streaming form: the fused circularity + peak kernel with no shared memory and no barriers.
+ *
+ * A warp walks DOWN a strip of the image, lane = column.  Per row it loads two SAT values per lane (columns u = x+1 and
+ * u+k), forms the box sum Q(u, v) = S(u+k,v+k) - S(u+k,v) - S(u,v+k) + S(u,v) against the values it loaded k rows
+ * earlier (register ring), fetches Q(x-R, v) from the lane R+1 to its left (one shuffle), and combines the Q rows v and
+ * v-R-1 (ring) into the circularity of row y = v-1:
+ *     pp = Q(x+1,y+1)  nn = Q(x-R,y-R)  pn = -Q(x+1,y-R)  np = -Q(x-R,y+1)      (satBlobCenter.cl:37-41)
+ * The last three circularity rows stay in registers for the 4-neighbour peak test of row y-1 (left/right neighbours by
+ * shuffle).  All rings have depth R+2 and the row loop is unrolled by R+2, so every ring index is a compile-time
+ * constant.  ~25 instructions per lane and row; lanes 0..R+1 and 31 only feed their neighbours (strip = 29-R columns).
+ * Exactness: as for the tiled form above (box sums of exact integers, exact 3-operation division); pixels within R of
+ * the image border and flagged frames take the literal 16-tap form with IEEE division. */
+template <int R>
+__global__ void __launch_bounds__(128, 6) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
+                                                     int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
+                                                     const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                                                     uint32_t* __restrict__ masks, int wpr)
+{
+	constexpr int K = R - 1, D = R + 2;
+	constexpr int LO = R + 2;          /* first output lane: needs Q from lane-(R+1) and a circularity from lane-1 */
+	constexpr int SWU = 32 - LO - 1;   /* output lanes LO..30 */
+	constexpr float DIV = (float)(R * R);
+	constexpr float RCP = 1.0f / DIV;
+	const int lane = threadIdx.x & 31;
+	const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
+	const int f = blockIdx.z;
+	const int xs = strip * SWU;
+	if (xs >= w)
+		return;
+	const int x = xs + lane - LO;                       /* this lane's pixel column (may be outside the image) */
+	const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+	const size_t fbase = (size_t)f * w * h;
+	const float* satf = sat + fbase;
+	float* circf = circ_out + fbase;
+	const bool flagged = flag[f] != 0;
+	/* SAT columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
+	 * pixels would use (they take the 16-tap path), so u is merely kept inside the row: the u+K load may run up to K
+	 * floats past the row end, which stays inside the (padded) SAT scratch. */
+	const int ua = clampi(x + 1, 0, w - 1);
+	const bool x_in = x >= 0 && x < w;
+	const bool lane_fast = !flagged && x - R >= 0 && x + R <= w - 1;
+	const bool out_lane = lane >= LO && lane <= 30 && x < w; /* x >= 0 follows from lane >= LO */
+
+	float sa[D], sb[D], ta[K > 0 ? K : 1], tb[K > 0 ? K : 1], qa[D], qb[D], cr[D];
+#pragma unroll
+	for (int i = 0; i < D; i++)
+		sa[i] = sb[i] = qa[i] = qb[i] = cr[i] = 0.f;
+	int nb = 0, ns = 0, npk = 0;
+	const int t0 = ys - 1 - R, t1 = ye + R;
+	const float* pa = satf + ua;
+	float* pc = circf + x; /* only dereferenced for ys <= y < ye on output lanes */
+	for (int t = t0; t <= t1; t += D) {
+		/* keep the last K SAT rows of the previous group, then issue all 2*D loads of this group before the first one is
+		 * consumed (the walk would otherwise pay one L2 round trip per row) */
+#pragma unroll
+		for (int i = 0; i < K; i++) {
+			ta[i] = sa[D - K + i];
+			tb[i] = sb[D - K + i];
+		}
+		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: no row of the group is clamped */
+			const float* p = elem_ptr(pa, (unsigned)(t * w));
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				sa[s] = __ldg(p);
+				sb[s] = __ldg(p + K);
+				p += w;
+			}
+		} else { /* CLAMP_TO_EDGE in y: rows outside the image repeat the edge row */
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
+				sa[s] = __ldg(p);
+				sb[s] = __ldg(p + K);
+			}
+		}
+#pragma unroll
+		for (int s = 0; s < D; s++) {
+			const int tt = t + s; /* SAT row of this step */
+			if (tt > t1)
+				break;
+			/* Q row v = tt - K: SAT row v is in this group (slot s-K) or among the last K rows of the previous one */
+			constexpr int DD = 4 * D;
+			const int so = (s - K + DD) % D;             /* Q ring slot of row v */
+			const int sq = (s - 2 * R + DD) % D;         /* slot of Q row v-R-1 */
+			const int sc = (s - R + DD) % D;             /* slot of circularity row y */
+			const int sm = (s - R - 1 + DD) % D;         /* ... of row y-1 */
+			const int su = (s - R - 2 + DD) % D;         /* ... of row y-2 */
+			const float sa_old = s - K >= 0 ? sa[s - K >= 0 ? s - K : 0] : ta[s - K >= 0 ? 0 : s];
+			const float sb_old = s - K >= 0 ? sb[s - K >= 0 ? s - K : 0] : tb[s - K >= 0 ? 0 : s];
+			const float q = __fadd_rn(__fsub_rn(__fsub_rn(sb[s], sb_old), sa[s]), sa_old);
+			qa[so] = q;
+			qb[so] = __shfl_up_sync(0xffffffffu, q, R + 1);
+			const int y = tt - R; /* circularity row of this step (v - 1) */
+			if (y >= ys - 1) { /* uniform: earlier rows only warm the rings up */
+				float c = 0.f;
+				if (lane_fast && (unsigned)(y - R) <= (unsigned)(h - 1 - 2 * R)) {
+					const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
+					const float q0 = __fmul_rn(m, RCP);
+					c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0);
+				} else if (x_in && lane >= LO - 1 && y >= 0 && y < h) { /* border pixel whose value is used */
+					c = circle_px_generic(satf, w, h, x, y, R);
+				}
+				cr[sc] = c;
+				if (out_lane && (unsigned)(y - ys) < (unsigned)(ye - ys))
+					*elem_ptr(pc, (unsigned)(y * w)) = c;
+				/* peak test of row yy = y - 1 (blobList.cl:38-81) */
+				const int yy = y - 1;
+				const float cm = cr[sm];
+				const bool cand = out_lane && (unsigned)(yy - ys) < (unsigned)(ye - ys) && !(cm < thr);
+				if (__any_sync(0xffffffffu, cand)) {
+					const float cl = __shfl_up_sync(0xffffffffu, cm, 1), crr = __shfl_down_sync(0xffffffffu, cm, 1);
+					int cls = 0;
+					if (cand) {
+						const float up = yy > 0 ? cr[su] : cm, dn = yy < h - 1 ? c : cm; /* clamped neighbours equal the centre */
+						const float lf = x > 0 ? cl : cm, rt = x < w - 1 ? crr : cm;
+						if (lf > cm || rt > cm || up > cm || dn > cm)
+							cls = 1;
+						else
+							cls = need_score ? classify_by_score(flat + fbase, w, h, x, yy, radius, cm, min_score) : 3;
+						if (cls == 3) {
+							atomicOr(masks + ((size_t)f * h + yy) * wpr + (x >> 5), 1u << (x & 31));
+							atomicAdd(rowcount + f * h + yy, 1);
+						}
+					}
+					nb += __popc(__ballot_sync(0xffffffffu, cls == 3));
+					ns += __popc(__ballot_sync(0xffffffffu, cls == 2));
+					npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
+				}
+			}
+		}
 	}
 	publish_counters(lane, counter + 3 * f, nb, ns, npk);
 }

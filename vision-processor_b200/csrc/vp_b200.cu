@@ -75,6 +75,7 @@ struct vp_ctx {
 	size_t rows_cap = 0, frames_cap = 0, mask_words_cap = 0;
 	int group = 0; /* 0 = choose from the frame size */
 	bool staged_reproject = true;
+	bool stream_circ = true;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
 
@@ -320,7 +321,7 @@ int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames, siz
 		ctx->scratch_px = 0;
 		for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
 			CK(ctx, cudaMalloc(&ctx->rowsum[l], group_px * 4));
-			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4));
+			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4 + 256)); /* k_circ_stream reads up to R-1 floats past a row end */
 		}
 		ctx->scratch_px = group_px;
 	}
@@ -579,6 +580,13 @@ int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memor
 {
 	REQUIRE(ctx, ctx, "ctx is null");
 	ctx->staged_reproject = on != 0;
+	return VP_OK;
+}
+
+int vp_ctx_set_stream_circ(vp_ctx* ctx, int on) /* A/B switch: register-streaming vs shared-memory tiled circularity+peaks */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->stream_circ = on != 0;
 	return VP_OK;
 }
 
@@ -1124,16 +1132,31 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		}
 		if (fused_circ) {
 			Stage st(ctx, "circ_peaks", 1, s);
-			const dim3 grid(cdiv(wf, CT_W), cdiv(hf, CT_H), g);
+			if (ctx->stream_circ) {
+				const int seg = 128;
+#define VP_CS(RR)                                                                                                              \
+	case RR: {                                                                                                                 \
+		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, seg), g);                                                             \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
+		                                       rowcount, masks, wpr);                                                          \
+	} break;
+				switch (p->circle_radius) {
+					VP_CS(1) VP_CS(2) VP_CS(3) VP_CS(4) VP_CS(5) VP_CS(6) VP_CS(7) VP_CS(8) VP_CS(9) VP_CS(10) VP_CS(11) VP_CS(12)
+				}
+#undef VP_CS
+			} else {
+				const dim3 grid(cdiv(wf, CT_W), cdiv(hf, CT_H), g);
 #define VP_CP(RR)                                                                                                              \
 	case RR:                                                                                                                   \
 		k_circ_peaks<RR><<<grid, 256, 0, s>>>(sat, circ, flat, wf, hf, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
 		                                      rowcount, masks, wpr);                                                           \
 		break;
-			switch (p->circle_radius) {
-				VP_CP(1) VP_CP(2) VP_CP(3) VP_CP(4) VP_CP(5) VP_CP(6) VP_CP(7) VP_CP(8) VP_CP(9) VP_CP(10) VP_CP(11) VP_CP(12)
-			}
+				switch (p->circle_radius) {
+					VP_CP(1) VP_CP(2) VP_CP(3) VP_CP(4) VP_CP(5) VP_CP(6) VP_CP(7) VP_CP(8) VP_CP(9) VP_CP(10) VP_CP(11) VP_CP(12)
+				}
 #undef VP_CP
+			}
 			if ((rc = check_launch(ctx, "k_circ_peaks"))) return rc;
 		} else { /* radius outside the specialised range: unfused circle + count */
 			Stage st(ctx, "circle+count", 2, s);
