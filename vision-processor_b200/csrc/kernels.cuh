@@ -9,7 +9,7 @@
  * NV12 is produced per 2x2 block, and the blob list is compacted deterministically in raster order
  * (count -> rank -> emit) instead of through a racing atomic counter.
  *
- * Canonical arithmetic (shared with oracle/vp_oracle.c): fp32, every operation
+ * Canonical arithmetic (the one the CPU checker under oracle/ restates): fp32, every operation
  * individually rounded to nearest-even, no FMA contraction (explicit __f*_rn intrinsics and
  * -fmad=false), IEEE division and square root.
  */
