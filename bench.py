@@ -58,8 +58,8 @@ def algorithmic_bytes(lp, blobs_per_frame: float) -> dict:
         "reproject": 4 * nq + 4 * nf,          # raw in, flat out
         "grad_rowscan": 4 * nf + 8 * nf,       # flat in, gradDot + row sums out
         "colscan": 8 * nf,                     # row sums in, SAT out
-        "circle": 8 * nf,                      # SAT in, blobCenter out
-        "blob_list": 4 * nf,                   # blobCenter in (+ sparse flat reads, records)
+        "circ_peaks": 8 * nf,                  # SAT in, blobCenter out (+ blob bit masks)
+        "peaks_emit": 22 * blobs_per_frame,    # sparse: records out
     }
 
 
@@ -71,7 +71,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="frames per step and per GPU")
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = automatic)")
+    ap.add_argument("--lanes", type=int, default=0, help="streams the groups are spread over (0 = library default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -223,6 +224,8 @@ def main():
 
     ctx = lib.Context(local_rank)
     ctx.set_group(args.group)
+    if args.lanes:
+        ctx.set_lanes(args.lanes)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def step():

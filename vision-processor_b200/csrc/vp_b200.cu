@@ -64,7 +64,7 @@ struct vp_ctx {
 	cudaStream_t lane_stream[MAX_LANES] = {}; /* [0] aliases `stream` */
 	cudaEvent_t lane_done[MAX_LANES] = {};
 	cudaEvent_t fork = nullptr;
-	int lanes = 3;
+	int lanes = 2;
 	int32_t* rowsum[MAX_LANES] = {};
 	float* sat[MAX_LANES] = {};
 	size_t scratch_px = 0;
@@ -420,11 +420,11 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 {
 	if (ctx->group > 0)
 		return ctx->group < n_frames ? ctx->group : n_frames;
-	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over
-	 * one or two frames are launch- and tail-bound.  Groups of ~8 frames (10 Mpx) keep every kernel several waves long while
-	 * `lanes` groups in flight on separate streams let the issue-bound reprojection of one group overlap the bandwidth-bound
-	 * scans of another. */
-	size_t g = (size_t)10 * 1024 * 1024 / nf;
+	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over a
+	 * few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set
+	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau.  Two lanes (streams) with one group each in flight
+	 * cover the launch gaps and tails of one group with the other's kernels. */
+	size_t g = (size_t)40 * 1024 * 1024 / nf;
 	if (g < 1) g = 1;
 	if (g > 64) g = 64;
 	const size_t per_lane = ((size_t)n_frames + lanes - 1) / lanes;
@@ -820,6 +820,11 @@ int vp_raw2quad(vp_ctx* ctx, const vp_buf* raw, int fmt, int wq, int hq, vp_img*
 	REQUIRE(ctx, w2 == wq && h2 == hq && wq > 0 && hq > 0, "plane size %dx%d does not match %dx%d", w2, h2, wq, hq);
 	REQUIRE(ctx, raw->size >= (size_t)wq * hq * vp_format_pixel_size(fmt), "raw buffer too small");
 	CK(ctx, cudaSetDevice(ctx->device));
+	if (raw->mapped & VP_MAP_WRITE) {
+		/* A frame source that keeps its buffers mapped for the life of the driver and lets the camera SDK write into them
+		 * (spinnakerdriver.cpp:120-133) never unmaps: take the host mirror as it is now, stream-ordered. */
+		CK(ctx, cudaMemcpyAsync(raw->d, raw->h, raw->size, cudaMemcpyHostToDevice, ctx->stream));
+	}
 	Stage st(ctx, "raw2quad");
 	if (fmt == VP_FMT_BGR8) {
 		const int n = wq * hq;
