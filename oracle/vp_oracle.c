@@ -24,6 +24,9 @@ int vpo_get_threads(void) { return g_threads; }
 
 static inline int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+/* OpenCL C 6.12.4 min(x, y): "returns y if y < x, otherwise x" (not fminf: differs for (+0, -0) and NaN) */
+static inline float min_cl(float x, float y) { return y < x ? y : x; }
+
 /* ------------------------------------------------------------------ raw2quad */
 
 /* kernel/raw2quad.cl:21-39; NDRange (img.width, img.height) Resources.cpp:142 */
@@ -259,7 +262,7 @@ void vpo_circle(const float* sat, int w, int h, int r, float* out)
 			const float pn = ((mr[xp] - m1[xp]) - mr[x1]) + m1[x1]; /* :38 */
 			const float np = ((rp[xr] - r1[xr]) - rp[xm]) + r1[xm]; /* :39 */
 			const float nn = ((mr[xr] - m1[xr]) - mr[xm]) + m1[xm]; /* :40 */
-			out[x + (size_t)y * w] = fminf(fminf(pp, nn), fminf(pn, np)) / div; /* :41 */
+			out[x + (size_t)y * w] = min_cl(min_cl(pp, nn), min_cl(pn, np)) / div; /* :41 */
 		}
 	}
 }
@@ -407,7 +410,7 @@ void vpo_circularize(const float* in, int w, int h, int min_blob_radius, int max
 			nn /= fn;
 			pn /= fn;
 			np /= fn;
-			out[px + (size_t)py * w] = fminf(fminf(pp, nn), fminf(-pn, -np));
+			out[px + (size_t)py * w] = min_cl(min_cl(pp, nn), min_cl(-pn, -np));
 		}
 }
 

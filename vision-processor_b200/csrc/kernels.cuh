@@ -33,6 +33,9 @@ constexpr int SAT_EXACT_LIMIT = 1 << 22;
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+/* OpenCL C 6.12.4 min(x, y): "returns y if y < x, otherwise x" -- differs from fminf for (+0, -0) and NaN */
+__device__ __forceinline__ float min_cl(float x, float y) { return y < x ? y : x; }
+
 /* &base[idx] as ONE instruction (IMAD.WIDE.U32): nvcc otherwise expands pointer + 32-bit index into a 4-instruction
  * 64-bit add/shift sequence and rematerialises the base, which matters in kernels that are issue-bound */
 template <class T>
@@ -823,7 +826,7 @@ __device__ __forceinline__ float circle_px(const float* __restrict__ sat, int w,
 	const float pn = __fadd_rn(__fsub_rn(__fsub_rn(__ldg(mr + xp), __ldg(m1 + xp)), __ldg(mr + x1)), __ldg(m1 + x1));
 	const float np = __fadd_rn(__fsub_rn(__fsub_rn(__ldg(rp + xr), __ldg(r1 + xr)), __ldg(rp + xm)), __ldg(r1 + xm));
 	const float nn = __fadd_rn(__fsub_rn(__fsub_rn(__ldg(mr + xr), __ldg(m1 + xr)), __ldg(mr + xm)), __ldg(m1 + xm));
-	return __fdiv_rn(fminf(fminf(pp, nn), fminf(pn, np)), div);
+	return __fdiv_rn(min_cl(min_cl(pp, nn), min_cl(pn, np)), div);
 }
 
 __global__ void __launch_bounds__(256) k_circle(const float* __restrict__ sat, float* __restrict__ out, int w, int h, int r)
@@ -1409,7 +1412,7 @@ __global__ void __launch_bounds__(256) k_circularize(const float* __restrict__ i
 	nn = __fdiv_rn(nn, fn);
 	pn = __fdiv_rn(pn, fn);
 	np = __fdiv_rn(np, fn);
-	out[(size_t)py * w + px] = fminf(fminf(pp, nn), fminf(-pn, -np));
+	out[(size_t)py * w + px] = min_cl(min_cl(pp, nn), min_cl(-pn, -np));
 }
 
 /* ------------------------------------------------------------------------------------------------
