@@ -287,8 +287,13 @@ def main():
     frames_per_launch = B * n_prof_steps / per_stage[top][1]  # frames of the profiled pass / launches of that kernel
     avg_ms = per_stage[top][0] / per_stage[top][1]
     achieved = abytes[top] * frames_per_launch / (avg_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per frame of each kernel from the ncu --set full capture of round 1
+    # (profiles/r01_ncu_summary.txt, 16-frame launches), scaled to the frames one launch of this run processes
+    ncu_dram_bytes_per_frame = {"reproject": (90.963200e6 + 50.066688e6) / 16, "grad_rowscan": (81.103104e6 + 107.907840e6) / 16,
+                                "colscan": (80.238080e6 + 40.717056e6) / 16, "circ_peaks": (81.146368e6 + 37.956864e6) / 16}
+    traffic = ncu_dram_bytes_per_frame[top] * frames_per_launch if top in ncu_dram_bytes_per_frame else None
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[top] * frames_per_launch,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[top] * frames_per_launch,
                 "avg_launch_ms": avg_ms, "share_of_step": per_stage[top][0] / total_ms}
     pipeline_gbs = abytes["frame"] * (value / world) / 1e9
     stage_ms = {k: {"ms_per_frame": v[0] / (B * n_prof_steps), "share": v[0] / total_ms} for k, v in per_stage.items()}
