@@ -1118,8 +1118,53 @@ __global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sa
  * constant.  ~25 instructions per lane and row; lanes 0..R+1 and 31 only feed their neighbours (strip = 29-R columns).
  * Exactness: as for the tiled form above (box sums of exact integers, exact 3-operation division); pixels within R of
  * the image border and flagged frames take the literal 16-tap form with IEEE division. */
+/* circularity of the pixels within r of the image border (CLAMP_TO_EDGE acts on their taps): literal 16-tap form, one
+ * thread per pixel of the border frame (2.1 % of a 1224x1024 image).  Runs before k_circ_stream, which reads these values
+ * back instead of computing them in divergent lanes. */
+__global__ void __launch_bounds__(256) k_circ_border(const float* __restrict__ sat, float* __restrict__ circ_out, int w, int h, int r,
+                                                     const int* __restrict__ flag)
+{
+	const int f = blockIdx.y;
+	if (flag[f] != 0)
+		return; /* flagged frames are computed entirely by the generic path of k_circ_stream */
+	const int id = blockIdx.x * 256 + threadIdx.x;
+	const int rr = min(r, h / 2), rc = min(r, w / 2); /* border thickness if the image is smaller than 2r */
+	const int top = rr * w, mid_h = h - 2 * rr;
+	int x, y;
+	if (id < top) {
+		y = id / w;
+		x = id - y * w;
+	} else if (id < 2 * top) {
+		const int k = id - top;
+		y = k / w;
+		x = k - y * w;
+		y += h - rr;
+	} else {
+		const int k = id - 2 * top;
+		if (k >= mid_h * 2 * rc)
+			return;
+		y = k / (2 * rc);
+		const int c = k - y * 2 * rc;
+		y += rr;
+		x = c < rc ? c : w - 2 * rc + c;
+	}
+	const size_t fbase = (size_t)f * w * h;
+	circ_out[fbase + y * w + x] = circle_px(sat + fbase, w, h, x, y, r, (float)(r * r));
+}
+
+/* peak test of one pixel given its circularity and its four (already clamped) neighbours: blobList.cl:38-81 */
+__device__ __forceinline__ int classify_px(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, float thr, float min_score,
+                                           int need_score, float cm, float lf, float rt, float up, float dn)
+{
+	if (cm < thr)
+		return 0;
+	if (lf > cm || rt > cm || up > cm || dn > cm)
+		return 1;
+	return need_score ? classify_by_score(img, w, h, x, y, radius, cm, min_score) : 3;
+}
+
 template <int R>
-__global__ void __launch_bounds__(128, 6) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
+__global__ void __launch_bounds__(128) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
                                                      int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
                                                      const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
                                                      uint32_t* __restrict__ masks, int wpr)
@@ -1140,100 +1185,163 @@ __global__ void __launch_bounds__(128, 6) k_circ_stream(const float* __restrict_
 	const size_t fbase = (size_t)f * w * h;
 	const float* satf = sat + fbase;
 	float* circf = circ_out + fbase;
-	const bool flagged = flag[f] != 0;
-	/* SAT columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
-	 * pixels would use (they take the 16-tap path), so u is merely kept inside the row: the u+K load may run up to K
-	 * floats past the row end, which stays inside the (padded) SAT scratch. */
-	const int ua = clampi(x + 1, 0, w - 1);
+	const uint32_t* flatf = flat + fbase;
 	const bool x_in = x >= 0 && x < w;
-	const bool lane_fast = !flagged && x - R >= 0 && x + R <= w - 1;
 	const bool out_lane = lane >= LO && lane <= 30 && x < w; /* x >= 0 follows from lane >= LO */
+	const bool used_lane = x_in && lane >= LO - 1;            /* output lanes and their left/right neighbours inside the image */
+	int nb = 0, ns = 0, npk = 0;
+	int32_t* rcf = rowcount + f * h;
+	uint32_t* mkf = masks + (size_t)f * h * wpr;
 
-	float sa[D], sb[D], ta[K > 0 ? K : 1], tb[K > 0 ? K : 1], qa[D], qb[D], cr[D];
+	auto publish = [&](int cls, int yy) { /* warp-uniform call */
+		if (cls == 3) {
+			atomicOr(mkf + (yy * wpr + (x >> 5)), 1u << (x & 31));
+			atomicAdd(rcf + yy, 1);
+		}
+		nb += __popc(__ballot_sync(0xffffffffu, cls == 3));
+		ns += __popc(__ballot_sync(0xffffffffu, cls == 2));
+		npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
+	};
+
+	if (flag[f] != 0) {
+		/* Flagged frame (a sum left the exactness bound): literal 16-tap form for every pixel, three rows in registers. */
+		float c2 = 0.f, c1 = 0.f;
+		for (int y = ys - 1; y <= ye; y++) {
+			float c = 0.f;
+			if (used_lane && y >= 0 && y < h)
+				c = circle_px_generic(satf, w, h, x, y, R);
+			if (out_lane && y >= ys && y < ye)
+				circf[y * w + x] = c;
+			const int yy = y - 1;
+			const bool cand = out_lane && yy >= ys && yy < ye && !(c1 < thr);
+			if (__any_sync(0xffffffffu, cand)) {
+				const float cl = __shfl_up_sync(0xffffffffu, c1, 1), crr = __shfl_down_sync(0xffffffffu, c1, 1);
+				const int cls = cand ? classify_px(flatf, w, h, x, yy, radius, thr, min_score, need_score, c1, x > 0 ? cl : c1, x < w - 1 ? crr : c1,
+				                                   yy > 0 ? c2 : c1, yy < h - 1 ? c : c1)
+				                     : 0;
+				publish(cls, yy);
+			}
+			c2 = c1;
+			c1 = c;
+		}
+		publish_counters(lane, counter + 3 * f, nb, ns, npk);
+		return;
+	}
+
+	/* SAT columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
+	 * pixels would use (those read the value k_circ_border computed), so u is merely kept inside the row: the u+K load may
+	 * run up to K floats past the row end, which stays inside the (padded) SAT scratch. */
+	const int ua = clampi(x + 1, 0, w - 1);
+	const bool lane_border = !(x - R >= 0 && x + R <= w - 1);
+	const bool warp_has_border_lane = __any_sync(0xffffffffu, used_lane && lane_border);
+	const float* pa = satf + ua;
+	float* pc = circf + (x_in ? x : 0);
+
+	/* H(t) = S(u+K, t) - S(u, t); Q(u, v) = H(v+K) - H(v).  (The reference evaluates ((S11 - S10) - S01) + S00; inside the
+	 * exactness bound every partial result is an exact integer below 2^24, so the order is irrelevant.) */
+	float la[D], lb[D], cb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D], cbc[D];
 #pragma unroll
 	for (int i = 0; i < D; i++)
-		sa[i] = sb[i] = qa[i] = qb[i] = cr[i] = 0.f;
-	int nb = 0, ns = 0, npk = 0;
-	const int t0 = ys - 1 - R, t1 = ye + R;
-	const float* pa = satf + ua;
-	float* pc = circf + x; /* only dereferenced for ys <= y < ye on output lanes */
-	for (int t = t0; t <= t1; t += D) {
-		/* keep the last K SAT rows of the previous group, then issue all 2*D loads of this group before the first one is
-		 * consumed (the walk would otherwise pay one L2 round trip per row) */
-#pragma unroll
-		for (int i = 0; i < K; i++) {
-			ta[i] = sa[D - K + i];
-			tb[i] = sb[D - K + i];
-		}
+		hn[i] = qa[i] = qb[i] = cr[i] = cb[i] = cbc[i] = 0.f;
+	const int t0 = ys - 1 - R;
+	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
+
+	/* loads of one group: D SAT rows (rows outside the image repeat the edge row: CLAMP_TO_EDGE in y) and, where the
+	 * group touches the image border, the circularities k_circ_border prepared for this lane's pixels */
+	auto load_group = [&](int t) {
 		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: no row of the group is clamped */
 			const float* p = elem_ptr(pa, (unsigned)(t * w));
 #pragma unroll
 			for (int s = 0; s < D; s++) {
-				sa[s] = __ldg(p);
-				sb[s] = __ldg(p + K);
+				la[s] = __ldg(p);
+				lb[s] = __ldg(p + K);
 				p += w;
 			}
-		} else { /* CLAMP_TO_EDGE in y: rows outside the image repeat the edge row */
+		} else {
 #pragma unroll
 			for (int s = 0; s < D; s++) {
 				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
-				sa[s] = __ldg(p);
-				sb[s] = __ldg(p + K);
+				la[s] = __ldg(p);
+				lb[s] = __ldg(p + K);
 			}
 		}
+		const int y0 = t - R; /* circularity rows of the group: y0 .. y0+D-1 */
+		if (warp_has_border_lane || y0 < R || y0 + D - 1 > h - 1 - R) { /* warp-uniform */
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				const int y = y0 + s;
+				if (used_lane && y >= 0 && y < h && (lane_border || y < R || y > h - 1 - R))
+					cb[s] = __ldcg(elem_ptr(pc, (unsigned)(y * w)));
+			}
+		}
+	};
+
+	load_group(t0);
+	for (int g = 0; g < n_groups; g++) {
+		const int t = t0 + g * D;
+		/* consume this group's loads, then put the next group's loads in flight before the arithmetic of this one */
+#pragma unroll
+		for (int i = 0; i < K; i++)
+			hold[i] = hn[D - K + i];
 #pragma unroll
 		for (int s = 0; s < D; s++) {
-			const int tt = t + s; /* SAT row of this step */
-			if (tt > t1)
-				break;
-			/* Q row v = tt - K: SAT row v is in this group (slot s-K) or among the last K rows of the previous one */
-			constexpr int DD = 4 * D;
-			const int so = (s - K + DD) % D;             /* Q ring slot of row v */
-			const int sq = (s - 2 * R + DD) % D;         /* slot of Q row v-R-1 */
-			const int sc = (s - R + DD) % D;             /* slot of circularity row y */
-			const int sm = (s - R - 1 + DD) % D;         /* ... of row y-1 */
-			const int su = (s - R - 2 + DD) % D;         /* ... of row y-2 */
-			const float sa_old = s - K >= 0 ? sa[s - K >= 0 ? s - K : 0] : ta[s - K >= 0 ? 0 : s];
-			const float sb_old = s - K >= 0 ? sb[s - K >= 0 ? s - K : 0] : tb[s - K >= 0 ? 0 : s];
-			const float q = __fadd_rn(__fsub_rn(__fsub_rn(sb[s], sb_old), sa[s]), sa_old);
+			hn[s] = __fsub_rn(lb[s], la[s]);
+			cbc[s] = cb[s];
+		}
+		if (g + 1 < n_groups)
+			load_group(t + D);
+
+		/* Straight-line code for the D rows of the group: the shuffles and the short dependent chains of different rows
+		 * overlap; ONE vote per group decides whether any pixel reaches the threshold at all (almost never), and only then
+		 * are the rows classified one by one. */
+		constexpr int DD = 4 * D;
+		const int y0 = t - R; /* circularity row of step 0 */
+		float crow[D + 2]; /* circularity rows y0-2 .. y0+D-1 */
+		crow[0] = cr[(0 - R - 2 + DD) % D];
+		crow[1] = cr[(0 - R - 1 + DD) % D];
+#pragma unroll
+		for (int s = 0; s < D; s++) {
+			const int so = (s - K + DD) % D, sq = (s - 2 * R + DD) % D, sc = (s - R + DD) % D;
+			const float h_old = s - K >= 0 ? hn[s - K >= 0 ? s - K : 0] : hold[s - K >= 0 ? 0 : s];
+			const float q = __fsub_rn(hn[s], h_old); /* Q row v = t+s-K */
 			qa[so] = q;
 			qb[so] = __shfl_up_sync(0xffffffffu, q, R + 1);
-			const int y = tt - R; /* circularity row of this step (v - 1) */
-			if (y >= ys - 1) { /* uniform: earlier rows only warm the rings up */
-				float c = 0.f;
-				if (lane_fast && (unsigned)(y - R) <= (unsigned)(h - 1 - 2 * R)) {
-					const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
-					const float q0 = __fmul_rn(m, RCP);
-					c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0);
-				} else if (x_in && lane >= LO - 1 && y >= 0 && y < h) { /* border pixel whose value is used */
-					c = circle_px_generic(satf, w, h, x, y, R);
-				}
-				cr[sc] = c;
-				if (out_lane && (unsigned)(y - ys) < (unsigned)(ye - ys))
-					*elem_ptr(pc, (unsigned)(y * w)) = c;
-				/* peak test of row yy = y - 1 (blobList.cl:38-81) */
-				const int yy = y - 1;
-				const float cm = cr[sm];
-				const bool cand = out_lane && (unsigned)(yy - ys) < (unsigned)(ye - ys) && !(cm < thr);
-				if (__any_sync(0xffffffffu, cand)) {
-					const float cl = __shfl_up_sync(0xffffffffu, cm, 1), crr = __shfl_down_sync(0xffffffffu, cm, 1);
-					int cls = 0;
-					if (cand) {
-						const float up = yy > 0 ? cr[su] : cm, dn = yy < h - 1 ? c : cm; /* clamped neighbours equal the centre */
-						const float lf = x > 0 ? cl : cm, rt = x < w - 1 ? crr : cm;
-						if (lf > cm || rt > cm || up > cm || dn > cm)
-							cls = 1;
-						else
-							cls = need_score ? classify_by_score(flat + fbase, w, h, x, yy, radius, cm, min_score) : 3;
-						if (cls == 3) {
-							atomicOr(masks + ((size_t)f * h + yy) * wpr + (x >> 5), 1u << (x & 31));
-							atomicAdd(rowcount + f * h + yy, 1);
-						}
+			const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
+			const float q0 = __fmul_rn(m, RCP);
+			float c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0); /* == m / (R*R), satBlobCenter.cl:41 */
+			const int y = y0 + s;
+			if (lane_border || y < R || y > h - 1 - R)
+				c = cbc[s]; /* border pixel: the value k_circ_border computed (unused lanes/rows carry garbage that is never read) */
+			cr[sc] = c;
+			crow[s + 2] = c;
+			if (out_lane && y >= ys && y < ye)
+				*elem_ptr(pc, (unsigned)(y * w)) = c;
+		}
+		/* rows classified by this group: yy = y0-1 .. y0+D-2, i.e. crow[1 .. D] */
+		float mx = crow[1];
+#pragma unroll
+		for (int s = 2; s <= D; s++)
+			mx = fmaxf(mx, crow[s]);
+		if (__any_sync(0xffffffffu, out_lane && !(mx < thr))) {
+#pragma unroll 1
+			for (int i = 1; i <= D; i++) {
+				const int yy = y0 + i - 2;
+				float cm = crow[1], up = crow[0], dn = crow[2];
+#pragma unroll
+				for (int k = 2; k <= D; k++)
+					if (i == k) {
+						cm = crow[k];
+						up = crow[k - 1];
+						dn = crow[k + 1];
 					}
-					nb += __popc(__ballot_sync(0xffffffffu, cls == 3));
-					ns += __popc(__ballot_sync(0xffffffffu, cls == 2));
-					npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
-				}
+				const bool cand = out_lane && yy >= ys && yy < ye && !(cm < thr);
+				if (!__any_sync(0xffffffffu, cand))
+					continue;
+				const float cl = __shfl_up_sync(0xffffffffu, cm, 1), crr = __shfl_down_sync(0xffffffffu, cm, 1);
+				const int cls = cand ? classify_px(flatf, w, h, x, yy, radius, thr, min_score, need_score, cm, x > 0 ? cl : cm, x < w - 1 ? crr : cm,
+				                                   yy > 0 ? up : cm, yy < h - 1 ? dn : cm)
+				                     : 0;
+				publish(cls, yy);
 			}
 		}
 	}

@@ -1136,9 +1136,15 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 			if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
 		}
 		if (fused_circ) {
-			Stage st(ctx, "circ_peaks", 1, s);
+			Stage st(ctx, "circ_peaks", ctx->stream_circ ? 2 : 1, s);
 			if (ctx->stream_circ) {
 				const int seg = 128;
+				{
+					const int r = p->circle_radius, rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
+					const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
+					if (n_border > 0)
+						k_circ_border<<<dim3(cdiv(n_border, 256), g), 256, 0, s>>>(sat, circ, wf, hf, r, flag);
+				}
 #define VP_CS(RR)                                                                                                              \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
