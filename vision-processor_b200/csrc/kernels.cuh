@@ -326,7 +326,7 @@ constexpr int TQ_W = 80, TQ_H = 24;   /* staged quads per plane (capacity) */
 struct TileEntry {
 	int ib, jb;     /* quad coordinate of staged texel (0,0); ib is a multiple of 8 */
 	int height;     /* staged quad rows needed (<= TQ_H) */
-	int flags;      /* bit 0: footprint fits and coordinates are finite; bit 1: no clamping needed and rows are 16-byte aligned */
+	int flags;      /* bit 0: footprint fits and coordinates are finite; bit 1: staging with 16-byte vectors is possible */
 };
 
 /* floor(u - 0.5) exactly as axis_setup_fast computes it */
@@ -386,8 +386,8 @@ __global__ void __launch_bounds__(256) k_tile_table(const float2* __restrict__ l
 		e.jb = any ? j0 : 0;
 		e.height = any ? j1 - j0 + 1 : 0;
 		const bool fits = any && all_finite && (long long)i1 - e.ib + 1 <= TQ_W && e.height <= TQ_H;
-		const bool inner = fits && e.ib >= 0 && e.ib + TQ_W <= wq && e.jb >= 0 && e.jb + e.height <= hq && (wq % 8) == 0;
-		e.flags = (fits ? 1 : 0) | (inner ? 2 : 0);
+		const bool vec = fits && (wq % 8) == 0; /* raw rows are 16-byte aligned and no 8-quad vector straddles the image edge */
+		e.flags = (fits ? 1 : 0) | (vec ? 2 : 0);
 		table[ty * gridDim.x + tx] = e;
 	}
 }
@@ -499,31 +499,39 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 
 	const int row_bytes = 2 * wq;
 	if (e.flags & 2) {
-		/* 16-byte vectors: raw row 2*jj + s holds planes (2s, 2s+1) of quad row jj interleaved */
+		/* 16-byte vectors: raw row 2*qy + s holds planes (2s, 2s+1) of quad row qy interleaved, 8 quads per vector.
+		 * CLAMP_TO_EDGE is resolved here: rows outside the image repeat the edge row; a vector entirely left (right) of the
+		 * image repeats the first (last) quad of the row -- ib and wq are multiples of 8, so no vector straddles the edge. */
 		constexpr int NV = TQ_W / 8;
 		const int total = NV * 2 * e.height;
-		const uint8_t* src = raw + (2 * e.jb * row_bytes + 2 * e.ib);
 		for (int v = tid; v < total; v += 256) {
 			const int rr = v / NV, cv = v - rr * NV;
-			const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + (rr * row_bytes + cv * 16)));
+			const int qy = clampi(e.jb + (rr >> 1), 0, hq - 1);
+			const int qx0 = e.ib + cv * 8;
+			const int qxc = clampi(qx0, 0, wq - 8);
+			uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((2 * qy + (rr & 1)) * row_bytes + 2 * qxc)));
+			if (qx0 != qxc) { /* replicate the edge quad's two bytes over the whole vector */
+				const uint32_t edge = qx0 < 0 ? (q.x & 0xFFFFu) : (q.w >> 16);
+				q.x = q.y = q.z = q.w = edge * 0x00010001u;
+			}
 			float* d0 = T + ((rr & 1) * 2 * TQ_H + (rr >> 1)) * TQ_W + cv * 8; /* plane 2s */
 			float* d1 = d0 + TQ_H * TQ_W;                                     /* plane 2s+1 */
 			const uint32_t wds[4] = { q.x, q.y, q.z, q.w };
-			float e0[8], e1[8];
+			float2 e0[4], e1[4];
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				e0[2 * k] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7440)), 8388608.0f);
-				e1[2 * k] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7441)), 8388608.0f);
-				e0[2 * k + 1] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7442)), 8388608.0f);
-				e1[2 * k + 1] = __fsub_rn(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7443)), 8388608.0f);
+			for (int k = 0; k < 4; k++) { /* bytes 0,2 -> plane 2s; bytes 1,3 -> plane 2s+1; 0x4B0000bb is the float 2^23 + b */
+				const float2 a = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7442)));
+				const float2 b = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7441)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7443)));
+				e0[k] = add2(a, make_float2(-8388608.0f, -8388608.0f));
+				e1[k] = add2(b, make_float2(-8388608.0f, -8388608.0f));
 			}
-			reinterpret_cast<float4*>(d0)[0] = make_float4(e0[0], e0[1], e0[2], e0[3]);
-			reinterpret_cast<float4*>(d0)[1] = make_float4(e0[4], e0[5], e0[6], e0[7]);
-			reinterpret_cast<float4*>(d1)[0] = make_float4(e1[0], e1[1], e1[2], e1[3]);
-			reinterpret_cast<float4*>(d1)[1] = make_float4(e1[4], e1[5], e1[6], e1[7]);
+			reinterpret_cast<float4*>(d0)[0] = make_float4(e0[0].x, e0[0].y, e0[1].x, e0[1].y);
+			reinterpret_cast<float4*>(d0)[1] = make_float4(e0[2].x, e0[2].y, e0[3].x, e0[3].y);
+			reinterpret_cast<float4*>(d1)[0] = make_float4(e1[0].x, e1[0].y, e1[1].x, e1[1].y);
+			reinterpret_cast<float4*>(d1)[1] = make_float4(e1[2].x, e1[2].y, e1[3].x, e1[3].y);
 		}
 	} else {
-		/* border tile: per-texel gather with the edge replicated (CLAMP_TO_EDGE resolved at staging time) */
+		/* rows not 16-byte aligned (wq % 8 != 0): per-texel gather with the edge replicated */
 		const int total = 4 * e.height * TQ_W;
 		for (int v = tid; v < total; v += 256) {
 			const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */

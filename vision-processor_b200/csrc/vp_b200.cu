@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1138,7 +1139,8 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		if (fused_circ) {
 			Stage st(ctx, "circ_peaks", ctx->stream_circ ? 2 : 1, s);
 			if (ctx->stream_circ) {
-				const int seg = 128;
+				static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
+				const int seg = seg_env > 0 ? seg_env : 128;
 				{
 					const int r = p->circle_radius, rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
 					const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
