@@ -56,7 +56,8 @@ def algorithmic_bytes(lp, blobs_per_frame: float) -> dict:
     return {
         "frame": 4 * nq + 4 * nf + 4 * nf + 4 * nf + 22 * blobs_per_frame + 12,
         "reproject": 4 * nq + 4 * nf,          # raw in, flat out
-        "grad_rowscan": 4 * nf + 8 * nf,       # flat in, gradDot + row sums out
+        "grad_sat": 4 * nf + 8 * nf,           # flat in, gradDot + SAT out (single pass)
+        "grad_rowscan": 4 * nf + 8 * nf,       # (two-pass alternative) flat in, gradDot + row sums out
         "colscan": 8 * nf,                     # row sums in, SAT out
         "circ_peaks": 8 * nf,                  # SAT in, blobCenter out (+ blob bit masks)
         "peaks_emit": 22 * blobs_per_frame,    # sparse: records out

@@ -221,6 +221,9 @@ VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
 /* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
  * tiled kernel; results are bit-identical */
 VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);
+/* A/B switch (default OFF: measured 6.8 vs 5.8 us/frame on B200): gradient + summed-area table in one pass (strip-resident in shared memory, aggregate
+ * look-back between strips) vs gradient+row scan followed by a column scan; results are bit-identical */
+VP_API int vp_ctx_set_fused_sat(vp_ctx* ctx, int on);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 VP_API uint64_t vp_launch_count(const vp_ctx* ctx);

@@ -24,6 +24,7 @@ ap.add_argument("--group", type=int, default=0)
 ap.add_argument("--lanes", type=int, default=2)
 ap.add_argument("--direct", action="store_true", help="direct-gather reprojection instead of the staged kernel")
 ap.add_argument("--tiled-circ", action="store_true", help="shared-memory tiled circularity kernel instead of the streaming one")
+ap.add_argument("--fused-sat", action="store_true", help="single-pass gradient+SAT kernel instead of row scan + column scan")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--times", action="store_true", help="print CUDA-event time per step and per stage")
@@ -47,6 +48,7 @@ ctx.set_group(args.group)
 ctx.set_lanes(args.lanes)
 ctx.set_staged_reproject(not args.direct)
 ctx.set_stream_circ(not args.tiled_circ)
+ctx.set_fused_sat(args.fused_sat)
 
 
 def step():

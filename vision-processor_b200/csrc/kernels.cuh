@@ -641,22 +641,14 @@ __global__ void k_gradient_dot(const uint32_t* __restrict__ in, float* __restric
  * consecutive pixels (16-byte loads/stores when wf % 4 == 0), local prefix + warp-shuffle scan + running
  * carry.  Writes gradDot (fp32, API output) and the int32 row sums (internal).  flag[frame] is raised when a
  * row sum leaves the exact range of fp32 (satHorizontal.cl:26-31 would start rounding). */
-constexpr int ROWSCAN_WARPS = 8;
-__global__ void __launch_bounds__(ROWSCAN_WARPS * 32) k_grad_rowscan(const uint32_t* __restrict__ flat, float* __restrict__ grad,
-                                                                     int32_t* __restrict__ rowsum, int wf, int hf, int o,
-                                                                     int* __restrict__ flag)
+/* gradient + exact row prefix sums of one image row by one warp; `srow` may point to global or shared memory.
+ * Returns true if a row sum left the exactness bound. */
+__device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, int y, int wf, int hf, int o, int lane, float* __restrict__ grow,
+                                             int32_t* __restrict__ srow)
 {
-	const int lane = threadIdx.x & 31;
-	const int y = blockIdx.x * ROWSCAN_WARPS + (threadIdx.x >> 5);
-	if (y >= hf)
-		return;
-	const size_t fbase = (size_t)blockIdx.y * wf * hf;
-	const uint32_t* img = flat + fbase;
-	const uint32_t* row = img + (size_t)y * wf;
-	const uint32_t* up = img + (size_t)min(y + o, hf - 1) * wf;
-	const uint32_t* dn = img + (size_t)max(y - o, 0) * wf;
-	float* grow = grad + fbase + (size_t)y * wf;
-	int32_t* srow = rowsum + fbase + (size_t)y * wf;
+	const uint32_t* row = img + y * wf;
+	const uint32_t* up = img + min(y + o, hf - 1) * wf;
+	const uint32_t* dn = img + max(y - o, 0) * wf;
 	const bool vec = (wf & 3) == 0;
 	int carry = 0;
 	bool bad = false;
@@ -711,8 +703,96 @@ __global__ void __launch_bounds__(ROWSCAN_WARPS * 32) k_grad_rowscan(const uint3
 			}
 		}
 	}
-	if (bad)
+	return bad;
+}
+
+constexpr int ROWSCAN_WARPS = 8;
+__global__ void __launch_bounds__(ROWSCAN_WARPS * 32) k_grad_rowscan(const uint32_t* __restrict__ flat, float* __restrict__ grad,
+                                                                     int32_t* __restrict__ rowsum, int wf, int hf, int o,
+                                                                     int* __restrict__ flag)
+{
+	const int lane = threadIdx.x & 31;
+	const int y = blockIdx.x * ROWSCAN_WARPS + (threadIdx.x >> 5);
+	if (y >= hf)
+		return;
+	const size_t fbase = (size_t)blockIdx.y * wf * hf;
+	if (row_gradscan(flat + fbase, y, wf, hf, o, lane, grad + fbase + y * wf, rowsum + fbase + y * wf))
 		flag[blockIdx.y] = 1;
+}
+
+/* K2, single pass: gradient + summed-area table of a strip of `srows` rows x full width per CTA (one warp per row).
+ *   1. row prefix sums into shared memory (never written to HBM), gradDot to global;
+ *   2. column scan inside the strip; the strip's last row (its column aggregates) is published to global memory;
+ *   3. the carry of strip b is the sum of the aggregates of strips 0..b-1 of the same frame -- they are published
+ *      without waiting on anybody, so there is no serial chain, only a wait for "all earlier strips have published";
+ *   4. SAT = local + carry, converted to fp32 (exact inside the bound) and written once.
+ * Traffic per frame: flat in (4Nf) + gradDot out (4Nf) + SAT out (4Nf) instead of 20Nf for row scan + column scan.
+ * Strip indices are handed out by an atomic ticket per frame, so a CTA only ever waits for CTAs that started before it
+ * (forward progress does not depend on the block scheduling order). */
+__global__ void __launch_bounds__(1024) k_grad_sat(const uint32_t* __restrict__ flat, float* __restrict__ grad, float* __restrict__ sat, int wf, int hf,
+                                                   int o, int srows, int n_strips, int* __restrict__ flag, int* __restrict__ ticket,
+                                                   int* __restrict__ ready, int32_t* __restrict__ agg)
+{
+	extern __shared__ int32_t tile[]; /* srows x wf row prefix sums, then strip-local SAT */
+	__shared__ int s_strip;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int f = blockIdx.y;
+	if (tid == 0)
+		s_strip = atomicAdd(ticket + f, 1);
+	__syncthreads();
+	const int b = s_strip;
+	const int y0 = b * srows;
+	const size_t fbase = (size_t)f * wf * hf;
+	bool bad = false;
+	if (warp < srows) {
+		const int y = y0 + warp;
+		int32_t* trow = tile + warp * wf;
+		if (y < hf) {
+			bad = row_gradscan(flat + fbase, y, wf, hf, o, lane, grad + fbase + y * wf, trow);
+		} else {
+			for (int x = lane; x < wf; x += 32)
+				trow[x] = 0;
+		}
+	}
+	__syncthreads();
+	const int nthreads = blockDim.x;
+	int32_t* my_agg = agg + ((size_t)f * n_strips + b) * wf;
+	for (int x = tid; x < wf; x += nthreads) {
+		int s = 0;
+		for (int r = 0; r < srows; r++) {
+			s += tile[r * wf + x];
+			tile[r * wf + x] = s;
+		}
+		__stcg(my_agg + x, s);
+	}
+	__threadfence();
+	__syncthreads();
+	volatile int* rdy = ready + (size_t)f * n_strips;
+	if (tid == 0)
+		atomicExch(ready + (size_t)f * n_strips + b, 1);
+	if (tid < b) {
+		while (rdy[tid] == 0)
+			__nanosleep(64);
+	}
+	__threadfence();
+	__syncthreads();
+	const int32_t* fagg = agg + (size_t)f * n_strips * wf;
+	float* fsat = sat + fbase;
+	for (int x = tid; x < wf; x += nthreads) {
+		int c = 0;
+		for (int k = 0; k < b; k++)
+			c += __ldcg(fagg + k * wf + x);
+		for (int r = 0; r < srows; r++) {
+			const int y = y0 + r;
+			if (y < hf) {
+				const int v = tile[r * wf + x] + c;
+				bad |= abs(v) >= SAT_EXACT_LIMIT;
+				fsat[y * wf + x] = (float)v;
+			}
+		}
+	}
+	if (bad)
+		flag[f] = 1;
 }
 
 /* K2b: column prefix sums of the row sums -> SAT (satVertical.cl:22-31), exact in int32 (a
@@ -1467,9 +1547,12 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 /* per-batch preparation of the compaction scratch: zero the row counts and the exactness flags; either zero the
  * counters (fused path, main.cpp:283-288) or remember counter[0] as the first output slot (stage API). */
 __global__ void k_peaks_prepare(int32_t* __restrict__ counter, int32_t* __restrict__ first_slot, int32_t* __restrict__ rowcount,
-                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag, uint32_t* __restrict__ masks, int n_mask_words)
+                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag, uint32_t* __restrict__ masks, int n_mask_words,
+                                int* __restrict__ sync_words = nullptr, int n_sync_words = 0)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	for (int k = i; k < n_sync_words; k += gridDim.x * blockDim.x)
+		sync_words[k] = 0; /* strip tickets and ready flags of k_grad_sat */
 	for (int k = i; k < n_mask_words; k += gridDim.x * blockDim.x)
 		masks[k] = 0u;
 	if (i < n_rows_total)

@@ -49,6 +49,7 @@ struct HostSlot {
 } // namespace
 
 struct vp_ctx {
+	static constexpr int MAX_LANES_DECL = 4;
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
@@ -77,6 +78,12 @@ struct vp_ctx {
 	int group = 0; /* 0 = choose from the frame size */
 	bool staged_reproject = true;
 	bool stream_circ = true;
+	bool fused_sat = false; /* measured slower than row scan + column scan on B200 (profiles/r01_fused_sat_sweep.txt); kept as an A/B option */
+	bool grad_sat_attr = false;
+	int32_t* agg[MAX_LANES_DECL] = {};  /* strip aggregates of k_grad_sat, per lane */
+	size_t agg_words = 0;
+	int* sync_words = nullptr;          /* per frame of a batch: strip ticket + ready flags */
+	size_t sync_cap = 0;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
 
@@ -550,6 +557,9 @@ void vp_ctx_destroy(vp_ctx* c)
 		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
 	}
 	if (c->fork) cudaEventDestroy(c->fork);
+	for (int l = 0; l < vp_ctx::MAX_LANES; l++)
+		cudaFree(c->agg[l]);
+	cudaFree(c->sync_words);
 	cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
 	if (c->flag_host) cudaFreeHost(c->flag_host);
 	free_slots(c);
@@ -588,6 +598,13 @@ int vp_ctx_set_stream_circ(vp_ctx* ctx, int on) /* A/B switch: register-streamin
 {
 	REQUIRE(ctx, ctx, "ctx is null");
 	ctx->stream_circ = on != 0;
+	return VP_OK;
+}
+
+int vp_ctx_set_fused_sat(vp_ctx* ctx, int on) /* A/B switch: single-pass gradient+SAT kernel vs row scan + column scan */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->fused_sat = on != 0;
 	return VP_OK;
 }
 
@@ -1071,6 +1088,39 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
+	/* single-pass gradient + SAT: a strip of srows rows x full width lives in shared memory */
+	int srows = (int)((200u * 1024u) / ((size_t)wf * 4));
+	if (srows > 32) srows = 32;
+	static const int srows_env = getenv("VP_SAT_ROWS") ? atoi(getenv("VP_SAT_ROWS")) : 0; /* tuning aid */
+	if (srows_env > 0 && srows_env < srows) srows = srows_env;
+	const int n_strips = srows > 0 ? cdiv(hf, srows) : 0;
+	const bool fused_sat = ctx->fused_sat && srows >= 8 && n_strips <= 1024;
+	if (fused_sat) {
+		const size_t need_agg = (size_t)G * n_strips * wf, need_sync = (size_t)n_frames * (1 + n_strips);
+		if (need_agg > ctx->agg_words) {
+			CK(ctx, cudaDeviceSynchronize());
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+				cudaFree(ctx->agg[l]);
+				ctx->agg[l] = nullptr;
+			}
+			ctx->agg_words = 0;
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++)
+				CK(ctx, cudaMalloc(&ctx->agg[l], need_agg * 4));
+			ctx->agg_words = need_agg;
+		}
+		if (need_sync > ctx->sync_cap) {
+			CK(ctx, cudaDeviceSynchronize());
+			cudaFree(ctx->sync_words);
+			ctx->sync_words = nullptr;
+			ctx->sync_cap = 0;
+			CK(ctx, cudaMalloc(&ctx->sync_words, need_sync * 4));
+			ctx->sync_cap = need_sync;
+		}
+		if (!ctx->grad_sat_attr) {
+			CK(ctx, cudaFuncSetAttribute(k_grad_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+			ctx->grad_sat_attr = true;
+		}
+	}
 	const float2* lut;
 	const TileEntry* tiles;
 	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, p->wq, p->hq, &lut, &tiles);
@@ -1081,7 +1131,8 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	{
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
-		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr);
+		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr,
+		                                                       fused_sat ? ctx->sync_words : nullptr, fused_sat ? n_frames * (1 + n_strips) : 0);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
 	if (lanes > 1) { /* fork: the other lanes start after everything already enqueued on the context stream */
@@ -1122,14 +1173,23 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 			}
 			if (rc) return rc;
 		}
-		{
-			Stage st(ctx, "grad_rowscan", 1, s);
-			k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
-			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
-		}
-		{
-			Stage st(ctx, "colscan", 1, s);
-			if ((rc = launch_colscan(ctx, s, rowsum, sat, wf, hf, g, flag))) return rc;
+		if (fused_sat) {
+			Stage st(ctx, "grad_sat", 1, s);
+			int* ticket = ctx->sync_words + f0;
+			int* ready = ctx->sync_words + n_frames + (size_t)f0 * n_strips;
+			k_grad_sat<<<dim3(n_strips, g), srows * 32, (size_t)srows * wf * 4, s>>>(flat, grad, sat, wf, hf, p->grad_offset, srows, n_strips, flag, ticket, ready,
+			                                                                      ctx->agg[lane]);
+			if ((rc = check_launch(ctx, "k_grad_sat"))) return rc;
+		} else {
+			{
+				Stage st(ctx, "grad_rowscan", 1, s);
+				k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
+				if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
+			}
+			{
+				Stage st(ctx, "colscan", 1, s);
+				if ((rc = launch_colscan(ctx, s, rowsum, sat, wf, hf, g, flag))) return rc;
+			}
 		}
 		{
 			Stage st(ctx, "sat_fix", 1, s);

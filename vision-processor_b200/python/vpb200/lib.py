@@ -118,6 +118,7 @@ def load() -> C.CDLL:
         "vp_ctx_set_lanes": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
         "vp_profiling_enable": (C.c_int, [vp, C.c_int]),
         "vp_profiling_count": (C.c_int, [vp]),
@@ -339,6 +340,9 @@ class Context:
 
     def set_stream_circ(self, on: bool):
         self._ck(self.lib.vp_ctx_set_stream_circ(self.h, int(on)))
+
+    def set_fused_sat(self, on: bool):
+        self._ck(self.lib.vp_ctx_set_fused_sat(self.h, int(on)))
 
     def set_lanes(self, n: int):
         self._ck(self.lib.vp_ctx_set_lanes(self.h, n))
