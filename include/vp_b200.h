@@ -212,7 +212,7 @@ VP_API int vp_host_free(void* p);
 /* tuning knob: frames per kernel launch group of the fused path (0 = automatic: the group's working set is kept
  * inside the 126 MB L2) */
 VP_API int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group);
-/* tuning knob: number of CUDA streams the frame groups of one batch are spread over (1..4, default 2) so that the
+/* tuning knob: number of CUDA streams the frame groups of one batch are spread over (1..4, default 3) so that the
  * issue-bound reprojection of one group overlaps the bandwidth-bound scans of another */
 VP_API int vp_ctx_set_lanes(vp_ctx* ctx, int lanes);
 /* A/B switch (default on): reprojection through the shared-memory staged kernel vs the direct-gather kernel; results

@@ -21,7 +21,7 @@ from vpb200 import lib  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--group", type=int, default=0)
-ap.add_argument("--lanes", type=int, default=2)
+ap.add_argument("--lanes", type=int, default=3)
 ap.add_argument("--direct", action="store_true", help="direct-gather reprojection instead of the staged kernel")
 ap.add_argument("--tiled-circ", action="store_true", help="shared-memory tiled circularity kernel instead of the streaming one")
 ap.add_argument("--fused-sat", action="store_true", help="single-pass gradient+SAT kernel instead of row scan + column scan")

@@ -66,7 +66,7 @@ struct vp_ctx {
 	cudaStream_t lane_stream[MAX_LANES] = {}; /* [0] aliases `stream` */
 	cudaEvent_t lane_done[MAX_LANES] = {};
 	cudaEvent_t fork = nullptr;
-	int lanes = 2;
+	int lanes = 3;
 	int32_t* rowsum[MAX_LANES] = {};
 	float* sat[MAX_LANES] = {};
 	size_t scratch_px = 0;
@@ -430,8 +430,8 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 		return ctx->group < n_frames ? ctx->group : n_frames;
 	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over a
 	 * few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set
-	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau.  Two lanes (streams) with one group each in flight
-	 * cover the launch gaps and tails of one group with the other's kernels. */
+	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau.  Three lanes (streams) with one group each in flight
+	 * cover the launch gaps and tails of one group with the other groups' kernels (profiles/r01_group_sweep.txt). */
 	size_t g = (size_t)40 * 1024 * 1024 / nf;
 	if (g < 1) g = 1;
 	if (g > 64) g = 64;
