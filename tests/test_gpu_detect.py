@@ -69,6 +69,49 @@ def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
     check_frame(got, 0, want)
 
 
+@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat"])
+@pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2),
+                                dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, max_blobs=64)])
+def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
+    """Every A/B switch selects a different kernel for the same stage (direct-gather vs staged reprojection, tiled vs
+    streaming circularity, two-pass vs single-pass SAT): both settings must give the oracle's bits."""
+    p, raw, _ = common.make_case(**kw)
+    want = port.detect(raw, p)
+    setter = getattr(ctx, "set_" + switch)
+    default = {"staged_reproject": True, "stream_circ": True, "fused_sat": False}[switch]
+    try:
+        for value in (not default, default):
+            setter(value)
+            got = ctx.detect(np.stack([raw, raw, raw]), common.to_vp(p))
+            np.testing.assert_array_equal(got["flat"], want["flat"])
+            np.testing.assert_array_equal(got["grad"], want["grad"])
+            common.assert_float_images_equal(got["circ"], want["circ"])
+            for i in range(3):
+                check_frame(got, i, want)
+    finally:
+        setter(default)
+
+
+def test_sat_fallback_through_every_kernel_variant(ctx, port):
+    """The >2^22 fallback (sequential-order SAT, literal 16-tap circularity) through the tiled and the single-pass variants."""
+    p, _, _ = common.make_case(wq=256, hq=256, scale_mm=4.0)
+    h, w = 2 * p.hq, 2 * p.wq
+    yy, xx = np.mgrid[0:h, 0:w]
+    raw = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
+    want = port.detect(raw, p)
+    try:
+        for stream_circ, fused_sat in [(False, False), (True, True), (False, True)]:
+            ctx.set_stream_circ(stream_circ)
+            ctx.set_fused_sat(fused_sat)
+            got = ctx.detect(raw, common.to_vp(p))
+            assert got["sat_fallbacks"] == 1
+            common.assert_float_images_equal(got["circ"], want["circ"])
+            check_frame(got, 0, want)
+    finally:
+        ctx.set_stream_circ(True)
+        ctx.set_fused_sat(False)
+
+
 def test_detect_batch_of_distinct_frames(ctx, port):
     """11 frames (not a multiple of the upload chunk or the launch group), each with its own noise seed."""
     frames, wants = [], []
