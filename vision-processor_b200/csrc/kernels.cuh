@@ -1252,7 +1252,7 @@ __device__ __forceinline__ int classify_px(const uint32_t* __restrict__ img, int
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
+__global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
                                                      int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
                                                      const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
                                                      uint32_t* __restrict__ masks, int wpr)
