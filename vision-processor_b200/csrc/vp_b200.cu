@@ -1309,6 +1309,21 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 	const int chunk = n_frames < 4 ? n_frames : 4; /* frames per upload: amortises launches, keeps latency low */
 	rc = ensure_slots(ctx, (size_t)chunk, raw_bytes, nf, blobs);
 	if (rc) return rc;
+	if (n_frames <= chunk) {
+		/* latency path (a camera delivering one frame at a time): everything in order on one stream, no cross-stream hops */
+		HostSlot& s = ctx->slots[0];
+		CK(ctx, cudaMemcpyAsync(s.raw, h_raw, (size_t)n_frames * raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		rc = vp_detect_batch_device(ctx, s.raw, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter);
+		if (rc) return rc;
+		if (blobs)
+			CK(ctx, cudaMemcpyAsync(h_matches, s.matches, (size_t)n_frames * blobs * 22, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaMemcpyAsync(h_counter, s.counter, (size_t)n_frames * 12, cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->last_flat = s.flat + (size_t)(n_frames - 1) * nf * 4;
+		ctx->last_grad = s.grad + (size_t)(n_frames - 1) * nf;
+		ctx->last_circ = s.circ + (size_t)(n_frames - 1) * nf;
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		return VP_OK;
+	}
 	int k = 0;
 	for (int f0 = 0; f0 < n_frames; f0 += chunk, k++) {
 		const int g = n_frames - f0 < chunk ? n_frames - f0 : chunk;
