@@ -215,9 +215,13 @@ VP_API int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group);
 /* tuning knob: number of CUDA streams the frame groups of one batch are spread over (1..4, default 3) so that the
  * issue-bound reprojection of one group overlaps the bandwidth-bound scans of another */
 VP_API int vp_ctx_set_lanes(vp_ctx* ctx, int lanes);
-/* A/B switch (default on): reprojection through the shared-memory staged kernel vs the direct-gather kernel; results
- * are bit-identical */
+/* A/B switch, results are bit-identical: 0 = direct-gather reprojection, 1 = shared-memory staged kernel (weights
+ * derived per frame), 2 (default) = staged kernel that keeps the frame-invariant weights of a tile in registers over a
+ * chunk of frames of the batch */
 VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
+/* tuning knob of variant 2: frames of a launch group one CTA processes with the same registers (0 = automatic: 8, fewer
+ * when the grid would not fill the GPU) */
+VP_API int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames);
 /* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
  * tiled kernel; results are bit-identical */
 VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);

@@ -55,8 +55,13 @@ def test_detect_unusual_geometry(ctx, port, scale_mul, dx, dy):
     try:
         direct = ctx.detect(raw, common.to_vp(p))
     finally:
-        ctx.set_staged_reproject(True)
+        ctx.set_staged_reproject(1)  # staged, per-frame weights
+        try:
+            staged = ctx.detect(raw, common.to_vp(p))
+        finally:
+            ctx.set_staged_reproject(2)
     np.testing.assert_array_equal(direct["flat"], want["flat"])
+    np.testing.assert_array_equal(staged["flat"], want["flat"])
 
 
 def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
@@ -73,14 +78,15 @@ def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
 @pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2),
                                 dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, max_blobs=64)])
 def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
-    """Every A/B switch selects a different kernel for the same stage (direct-gather vs staged reprojection, tiled vs
+    """Every A/B switch selects a different kernel for the same stage (direct-gather vs staged vs frame-invariant-hoisted reprojection, tiled vs
     streaming circularity, two-pass vs single-pass SAT): both settings must give the oracle's bits."""
     p, raw, _ = common.make_case(**kw)
     want = port.detect(raw, p)
     setter = getattr(ctx, "set_" + switch)
-    default = {"staged_reproject": True, "stream_circ": True, "fused_sat": False}[switch]
+    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False)}[switch]  # default last
+    default = values[-1]
     try:
-        for value in (not default, default):
+        for value in values:
             setter(value)
             got = ctx.detect(np.stack([raw, raw, raw]), common.to_vp(p))
             np.testing.assert_array_equal(got["flat"], want["flat"])
@@ -122,6 +128,36 @@ def test_detect_batch_of_distinct_frames(ctx, port):
     got = ctx.detect(np.stack(frames), common.to_vp(p), want_images=False)
     for i, w in enumerate(wants):
         check_frame(got, i, w)
+
+
+@pytest.mark.parametrize("chunk", [2, 4, 16])
+@pytest.mark.parametrize("kw", [dict(wq=128, hq=80, n_robots=2, n_balls=2), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2, n_robots=2, n_balls=1)])
+def test_hoisted_reprojection_over_frame_chunks(ctx, port, chunk, kw):
+    """The hoisted reprojection keeps a tile's weights in registers over `chunk` frames: 7 distinct frames in one launch
+    group through chunk sizes that divide, do not divide and exceed the group; full and partial tiles, 16-byte-aligned
+    and unaligned raw rows; every frame's flat image compared."""
+    frames, wants = [], []
+    for s in range(7):
+        p, raw, _ = common.make_case(seed=20 + s, **kw)
+        frames.append(raw)
+        wants.append(port.detect(raw, p))
+    vp = common.to_vp(p)
+    n, nf, rb = len(frames), p.wf * p.hf, frames[0].size
+    bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
+    ctx.set_hoist_chunk(chunk)
+    try:
+        ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                                bufs["m"].device_ptr, bufs["c"].device_ptr)
+        flat = bufs["flat"].read(np.uint8).reshape(n, p.hf, p.wf, 4)
+        counter = bufs["c"].read(np.int32).reshape(n, 3)
+    finally:
+        ctx.set_hoist_chunk(0)
+    for i, w in enumerate(wants):
+        np.testing.assert_array_equal(flat[i], w["flat"])
+        np.testing.assert_array_equal(counter[i], w["counter"])
+    for b in bufs.values():
+        b.release()
 
 
 def test_detect_blob_overflow_keeps_first_in_raster_order(ctx, port):

@@ -565,6 +565,285 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K1, frame-invariant form: the default of the batched path.
+ *
+ * Everything resampling.cl:52-80 computes before it touches a texel -- the projected position, the four filter axes, the
+ * sixteen weight products w = (1-a|a)*(1-b|b) and the tap addresses -- depends on the camera geometry only, not on the
+ * frame.  A CTA therefore owns one 64x16 flat tile for a CHUNK of frames of the same camera: each thread derives the
+ * weights (as packed fp32x2 pairs) and staged-plane offsets of its four pixels once, keeps them in registers, and so
+ * does the staging plan (which 16-byte raw vectors go where).  Per frame what remains is the arithmetic on the data:
+ * 16 LDS + 8 FMUL2 + 12 FADD + 2 FADD2 per pixel and the dRGB pack.  The raw vectors of frame f+1 are fetched before
+ * frame f is blended.  Same operations in the same order as k_reproject_staged / the oracle: bit-identical.
+ *
+ * The integer tail works on the biased words 0x4B000000 + v that the 2^23 add leaves behind (val in [0, 255.5) for
+ * weights in [0,1]): (x>>1) keeps the bias halved exactly (it is even), and 2r-g-b cancels it (resampling.cl:86-91).
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t drgb_biased(uint32_t r, uint32_t g, uint32_t b)
+{
+	const uint32_t s = r + g + b; /* bias 3B; 3x - s cancels it */
+	const uint32_t dr = (3u * r - s + 510u) >> 2, dg = (3u * g - s + 510u) >> 2, db = (3u * b - s + 510u) >> 2;
+	return dr | (dg << 8) | (db << 16) | 0xFF000000u;
+}
+
+constexpr int HP = TQ_W + 4;               /* row pitch of the staged planes: an odd number of 16-byte chunks (see the staging plan) */
+constexpr int HPLANE = TQ_H * HP;          /* floats per plane */
+constexpr int HT = 4 * HPLANE;             /* floats per plane buffer */
+constexpr int HNV = TQ_W / 8;              /* 16-byte raw vectors per staged row */
+constexpr int HRING = HNV * 2 * TQ_H * 16; /* bytes of one raw stage */
+constexpr size_t HOIST_SMEM = 2 * (size_t)HT * 4 + 2 * (size_t)HRING;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/* a + b as ONE packed instruction that ptxas cannot contract with the packed product feeding it: fma(a, 1, b) with a
+ * 1.0 the compiler cannot see (a kernel argument).  rn(a*1 + b) == rn(a + b) bit for bit.  With a literal 1.0 -- or a
+ * plain add.rn.f32x2 -- ptxas 12.9 folds the preceding mul.rn.f32x2 into an FFMA2 and the product loses its rounding. */
+__device__ __forceinline__ float2 add2_opaque(float2 a, float2 b, unsigned long long one2)
+{
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(one2), "l"(f2_bits(b)));
+	return bits_f2(r);
+}
+
+/* the per-frame arithmetic of one thread's four pixels (rows ly, ly+4, ly+8, ly+12 of the tile) */
+template <int FMT, bool FULL>
+__device__ __forceinline__ void hoist_blend(const float* __restrict__ T, const float2 (&W)[4][8], const int (&O)[4][4], uint32_t* __restrict__ out, int wf,
+                                            bool okx, int rows_ok, unsigned long long one2)
+{
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const float* t0 = T + O[k][0];
+		const float* t1 = T + O[k][1];
+		const float* t2 = T + O[k][2];
+		const float* t3 = T + O[k][3];
+		const float2 p00 = mul2(W[k][0], make_float2(t0[0], t1[0]));
+		const float2 p10 = mul2(W[k][1], make_float2(t0[1], t1[1]));
+		const float2 p01 = mul2(W[k][2], make_float2(t0[HP], t1[HP]));
+		const float2 p11 = mul2(W[k][3], make_float2(t0[HP + 1], t1[HP + 1]));
+		const float2 r00 = mul2(W[k][4], make_float2(t2[0], t3[0]));
+		const float2 r10 = mul2(W[k][5], make_float2(t2[1], t3[1]));
+		const float2 r01 = mul2(W[k][6], make_float2(t2[HP], t3[HP]));
+		const float2 r11 = mul2(W[k][7], make_float2(t2[HP + 1], t3[HP + 1]));
+		/* ((p00 + p10) + p01) + p11, every sum rounded on its own (resampling.cl's filter) */
+		const float2 va = add2_opaque(p11, add2_opaque(p01, add2_opaque(p10, p00, one2), one2), one2);
+		const float2 vb = add2_opaque(r11, add2_opaque(r01, add2_opaque(r10, r00, one2), one2), one2);
+		const float2 ra = add2(va, make_float2(8388608.0f, 8388608.0f)); /* RNE to integer in the mantissa */
+		const float2 rb = add2(vb, make_float2(8388608.0f, 8388608.0f));
+		const uint32_t v0 = __float_as_uint(ra.x), v1 = __float_as_uint(ra.y), v2 = __float_as_uint(rb.x), v3 = __float_as_uint(rb.y);
+		const uint32_t px = FMT == FMT_RGGB ? drgb_biased(v0, (v1 >> 1) + (v2 >> 1), v3) : drgb_biased(v1, (v0 >> 1) + (v3 >> 1), v2);
+		if (FULL || (okx && 4 * k < rows_ok))
+			out[(uint32_t)(4 * k) * (uint32_t)wf] = px;
+	}
+}
+
+/* 16 raw bytes (8 quads of one raw row = planes 2s | 2s+1 interleaved) -> 8 + 8 fp32 texels in the staged planes */
+__device__ __forceinline__ void hoist_convert(uint4 qq, int edge, float* __restrict__ d0)
+{
+	if (edge) { /* replicate the edge quad's two bytes over the whole vector (CLAMP_TO_EDGE left / right of the image) */
+		const uint32_t eq = edge == 1 ? (qq.x & 0xFFFFu) : (qq.w >> 16);
+		qq.x = qq.y = qq.z = qq.w = eq * 0x00010001u;
+	}
+	float* d1 = d0 + HPLANE;
+	const uint32_t wds[4] = { qq.x, qq.y, qq.z, qq.w };
+	float2 e0[4], e1[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) { /* bytes 0,2 -> plane 2s; bytes 1,3 -> plane 2s+1; 0x4B0000bb is the float 2^23 + b */
+		const float2 a = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7442)));
+		const float2 b = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7441)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7443)));
+		e0[k] = add2(a, make_float2(-8388608.0f, -8388608.0f));
+		e1[k] = add2(b, make_float2(-8388608.0f, -8388608.0f));
+	}
+	reinterpret_cast<float4*>(d0)[0] = make_float4(e0[0].x, e0[0].y, e0[1].x, e0[1].y);
+	reinterpret_cast<float4*>(d0)[1] = make_float4(e0[2].x, e0[2].y, e0[3].x, e0[3].y);
+	reinterpret_cast<float4*>(d1)[0] = make_float4(e1[0].x, e1[0].y, e1[1].x, e1[1].y);
+	reinterpret_cast<float4*>(d1)[1] = make_float4(e1[2].x, e1[2].y, e1[3].x, e1[3].y);
+}
+
+template <int V> struct IntC { static constexpr int value = V; };
+
+/* Pipeline of one CTA over its frames 0..n-1 (one barrier per frame, everything addressed statically by frame parity):
+ *   raw ring R[0], R[1]  (cp.async; a thread copies and later converts ITS OWN vectors: no cross-thread hand-over)
+ *   plane buffers T[0], T[1]  (fp32, ping-pong)
+ *   iteration f:  issue copy(f+2) -> R[f&1];  blend(f) from T[f&1];  wait copy(f+1);  convert(f+1): R[(f+1)&1] -> T[(f+1)&1];  barrier
+ * R[f&1] is free at the start of iteration f (this thread converted frame f out of it in iteration f-1); T[(f+1)&1] was
+ * last read by blend(f-1), which every warp has left before the barrier that ended iteration f-1.  A warp that has
+ * finished blending goes straight on to converting.
+ * Staging plan: lanes 2k and 2k+1 take vector k of two staged rows ONE pitch apart; the pitch is 21 chunks of 16 bytes,
+ * so the eight lanes of a store phase hit eight different bank groups (a pitch of 20 gave 2-way conflicts). */
+template <int FMT>
+__global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+                                                              const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq,
+                                                              int wf, int hf, int n_frames, int chunk, float one)
+{
+	extern __shared__ __align__(16) unsigned char hoist_smem[];
+	float* const T = reinterpret_cast<float*>(hoist_smem);
+	unsigned char* const ring = hoist_smem + 2 * (size_t)HT * 4;
+	const int tx = blockIdx.x, ty = blockIdx.y;
+	const int f0 = blockIdx.z * chunk;
+	const int n = min(n_frames, f0 + chunk) - f0;
+	const TileEntry e = table[ty * gridDim.x + tx];
+	const int tid = threadIdx.x;
+	const int lx = tid & 63, ly = tid >> 6;
+	const int gx = tx * FT_W + lx;
+	const uint32_t nfl = (uint32_t)wf * (uint32_t)hf;
+	const uint8_t* const raw = raw0 + (size_t)f0 * frame_stride;
+	float2 pos[4]; /* requested first: nothing below depends on them until the weights are derived */
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gy = ty * FT_H + ly + 4 * k;
+		pos[k] = make_float2(0.f, 0.f);
+		if (gx < wf && gy < hf)
+			pos[k] = __ldg(lut + (gy * wf + gx));
+	}
+
+	if (!(e.flags & 1)) { /* footprint does not fit: direct gather, frame by frame */
+#pragma unroll 1
+		for (int f = 0; f < n; f++) {
+			const uint8_t* rawf = raw + (size_t)f * frame_stride;
+			uint32_t* out = flat + (size_t)(f0 + f) * nfl;
+#pragma unroll 1
+			for (int k = 0; k < 4; k++) {
+				const int gy = ty * FT_H + ly + 4 * k;
+				if (gx < wf && gy < hf) {
+					const float2 pos = __ldg(lut + (gy * wf + gx));
+					uint32_t v;
+					if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
+						v = reproject_bayer_rte_fast<FMT>(rawf, wq, hq, pos.x, pos.y);
+					} else {
+						uint32_t r, g, b;
+						const SrcBayer s{ rawf, 2 * wq };
+						demosaic<FMT, MODE_RTE>(s, wq, hq, pos.x, pos.y, r, g, b);
+						v = drgb(r, g, b);
+					}
+					out[gy * wf + gx] = v;
+				}
+			}
+		}
+		return;
+	}
+
+	/* ---- frame-invariant staging plan: up to two 16-byte raw vectors per thread ---- */
+	const int row_bytes = 2 * wq;
+	const bool vec = (e.flags & 2) != 0;
+	const int n_rr = 2 * e.height; /* raw rows to stage: rr = 2*j + s -> staged row j of planes (2s, 2s+1) */
+	const uint8_t* s_src[2]; /* this thread's vector i in the next frame to copy */
+	int s_dst[2], s_edge[2]; /* s_edge < 0: no vector */
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		const int v = tid + 256 * i;
+		const int q4 = v / (4 * HNV), w = v - q4 * (4 * HNV);
+		const int half = w >= 2 * HNV ? 1 : 0, w2 = w - half * 2 * HNV;
+		const int cv = w2 >> 1, rr = 4 * q4 + half + 2 * (w2 & 1);
+		s_src[i] = raw;
+		s_dst[i] = 0;
+		s_edge[i] = -1;
+		if (vec && rr < n_rr) {
+			const int qy = clampi(e.jb + (rr >> 1), 0, hq - 1);
+			const int qx0 = e.ib + cv * 8;
+			const int qxc = clampi(qx0, 0, wq - 8);
+			s_src[i] = raw + ((2 * qy + (rr & 1)) * row_bytes + 2 * qxc);
+			s_dst[i] = (rr & 1) * 2 * HPLANE + (rr >> 1) * HP + cv * 8;
+			s_edge[i] = qx0 < 0 ? 1 : (qx0 != qxc ? 2 : 0);
+		}
+	}
+	unsigned char* const my_ring = ring + tid * 16; /* vector i of stage st: my_ring + st*HRING + i*4096 */
+	int to_copy = n;                                /* frames not yet requested */
+	auto issue_copy = [&](auto STAGE) {             /* next frame into R[STAGE]; always commits, possibly an empty group */
+		if (to_copy > 0) {
+#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				if (s_edge[i] >= 0)
+					cp_async16(my_ring + decltype(STAGE)::value * HRING + i * 4096, s_src[i]);
+				s_src[i] += frame_stride;
+			}
+		}
+		to_copy--;
+		cp_async_commit();
+	};
+	const uint8_t* gather_src = raw; /* unaligned path only: the next frame to convert */
+	auto convert = [&](auto PARC) { /* this thread's share of the next frame: R[PAR] -> T[PAR] */
+		constexpr int PAR = decltype(PARC)::value;
+		float* Tb = T + PAR * HT;
+		if (vec) {
+#pragma unroll
+			for (int i = 0; i < 2; i++)
+				if (s_edge[i] >= 0)
+					hoist_convert(*reinterpret_cast<const uint4*>(my_ring + PAR * HRING + i * 4096), s_edge[i], Tb + s_dst[i]);
+		} else { /* raw rows not 16-byte aligned (wq % 8 != 0): per-texel gather with the edge replicated */
+			const int tot = 4 * e.height * TQ_W;
+			for (int v = tid; v < tot; v += 256) {
+				const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
+				const int jj = rc >> 2, c = rc & 3;
+				const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
+				Tb[c * HPLANE + jj * HP + ii] = u8_to_float(__ldg(gather_src + ((2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1))));
+			}
+			gather_src += frame_stride;
+		}
+	};
+	issue_copy(IntC<0>{});
+	issue_copy(IntC<1>{});
+
+	/* ---- frame-invariant part: weights and tap offsets of this thread's four pixels (the copies are in flight) ---- */
+	float2 W[4][8];
+	int O[4][4];
+	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gy = ty * FT_H + ly + 4 * k;
+		const bool ok = gx < wf && gy < hf;
+		int ixp, ixn, iyp, iyn;
+		float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
+		axis_staged2(add2(make_float2(pos[k].x, pos[k].x), make_float2(0.25f, -0.25f)), xmagic, ixp, ixn, ax, ox);
+		axis_staged2(add2(make_float2(pos[k].y, pos[k].y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
+		/* planes 0 (+,+) | 1 (-,+) share the +y axis, planes 2 (+,-) | 3 (-,-) the -y axis */
+		const float2 ayp = make_float2(ay.x, ay.x), oyp = make_float2(oy.x, oy.x);
+		const float2 ayn = make_float2(ay.y, ay.y), oyn = make_float2(oy.y, oy.y);
+		W[k][0] = mul2(ox, oyp); W[k][1] = mul2(ax, oyp); W[k][2] = mul2(ox, ayp); W[k][3] = mul2(ax, ayp);
+		W[k][4] = mul2(ox, oyn); W[k][5] = mul2(ax, oyn); W[k][6] = mul2(ox, ayn); W[k][7] = mul2(ax, ayn);
+		O[k][0] = ok ? iyp * HP + ixp : 0; /* pixels outside the image read texel 0 and are not stored */
+		O[k][1] = ok ? HPLANE + iyp * HP + ixn : 0;
+		O[k][2] = ok ? 2 * HPLANE + iyn * HP + ixp : 0;
+		O[k][3] = ok ? 3 * HPLANE + iyn * HP + ixn : 0;
+	}
+	const bool okx = gx < wf;
+	const int rows_ok = hf - (ty * FT_H + ly);                        /* pixel k is inside the image iff 4k < rows_ok */
+	const bool full = (tx + 1) * FT_W <= wf && (ty + 1) * FT_H <= hf; /* CTA-uniform: no per-pixel predicates */
+	uint32_t* out = flat + (size_t)f0 * nfl + ((uint32_t)(ty * FT_H + ly) * (uint32_t)wf + (uint32_t)gx); /* pixel k adds 4*k*wf */
+	const unsigned long long one2 = f2_bits(make_float2(one, one));
+
+	cp_async_wait<1>();
+	convert(IntC<0>{});
+	__syncthreads();
+	int left = n; /* frames not yet blended */
+	auto iteration = [&](auto PARC) {
+		constexpr int PAR = decltype(PARC)::value;
+		issue_copy(PARC);
+		if (full)
+			hoist_blend<FMT, true>(T + PAR * HT, W, O, out, wf, true, 16, one2);
+		else
+			hoist_blend<FMT, false>(T + PAR * HT, W, O, out, wf, okx, rows_ok, one2);
+		out += nfl;
+		left--;
+		cp_async_wait<1>();
+		if (left > 0)
+			convert(IntC<PAR ^ 1>{});
+		__syncthreads();
+	};
+#pragma unroll 1
+	while (true) {
+		iteration(IntC<0>{});
+		if (left == 0) break;
+		iteration(IntC<1>{});
+		if (left == 0) break;
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
  * raw2quad.cl:21-39 (stage API only; the fused path never materialises the planes)
  * ---------------------------------------------------------------------------------------------- */
 __global__ void k_raw2quad_bayer(const uint8_t* __restrict__ raw, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1,

@@ -76,10 +76,14 @@ struct vp_ctx {
 	int* flag = nullptr;
 	size_t rows_cap = 0, frames_cap = 0, mask_words_cap = 0;
 	int group = 0; /* 0 = choose from the frame size */
-	bool staged_reproject = true;
+	int staged_reproject = 2; /* 0 direct gather, 1 staged per frame, 2 staged with frame-invariant weights hoisted */
+	int hoist_chunk = 0;      /* frames per CTA of the hoisted kernel; 0 = automatic */
+	int sm_count = 148;
 	bool stream_circ = true;
 	bool fused_sat = false; /* measured slower than row scan + column scan on B200 (profiles/r01_fused_sat_sweep.txt); kept as an A/B option */
 	bool grad_sat_attr = false;
+	bool hoist_attr = false;
+	volatile float one = 1.0f; /* handed to kernels that need a 1.0 the compiler cannot fold (add2_opaque) */
 	int32_t* agg[MAX_LANES_DECL] = {};  /* strip aggregates of k_grad_sat, per lane */
 	size_t agg_words = 0;
 	int* sync_words = nullptr;          /* per frame of a batch: strip ticket + ready flags */
@@ -501,6 +505,8 @@ int vp_ctx_create(int device, vp_ctx** out)
 		return fail(nullptr, VP_ERR_UNSUPPORTED, "device %d (%s) is sm_%d%d; this library is built for sm_100a only", device, prop.name, prop.major, prop.minor);
 	vp_ctx* c = new vp_ctx();
 	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	if (getenv("VP_HOIST_CHUNK")) c->hoist_chunk = atoi(getenv("VP_HOIST_CHUNK")); /* tuning aid */
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess
 	    || cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
@@ -590,7 +596,8 @@ int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group) /* tuning knob used by t
 int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memory staged vs direct-gather reprojection */
 {
 	REQUIRE(ctx, ctx, "ctx is null");
-	ctx->staged_reproject = on != 0;
+	REQUIRE(ctx, on >= 0 && on <= 2, "variant must be 0 (direct), 1 (staged) or 2 (staged, frame-invariant part hoisted)");
+	ctx->staged_reproject = on;
 	return VP_OK;
 }
 
@@ -605,6 +612,13 @@ int vp_ctx_set_fused_sat(vp_ctx* ctx, int on) /* A/B switch: single-pass gradien
 {
 	REQUIRE(ctx, ctx, "ctx is null");
 	ctx->fused_sat = on != 0;
+	return VP_OK;
+}
+
+int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames) /* frames one CTA of the hoisted reprojection keeps its weights for; 0 = automatic */
+{
+	REQUIRE(ctx, ctx && frames >= 0, "bad argument");
+	ctx->hoist_chunk = frames;
 	return VP_OK;
 }
 
@@ -1125,7 +1139,8 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	const TileEntry* tiles;
 	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, p->wq, p->hq, &lut, &tiles);
 	if (rc) return rc;
-	const bool staged = ctx->staged_reproject && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
+	const bool staged = ctx->staged_reproject != 0 && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
+	const bool hoisted = staged && ctx->staged_reproject == 2;
 	const int ns = need_score(p->circ_threshold, p->min_score);
 
 	{
@@ -1157,7 +1172,23 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		uint32_t* masks = ctx->masks + (size_t)f0 * hf * wpr;
 		{
 			Stage st(ctx, "reproject", 1, s);
-			if (staged) {
+			if (hoisted) {
+				/* one CTA keeps a tile's weights in registers for `chunk` frames; enough CTAs to fill the GPU several times */
+				int chunk = ctx->hoist_chunk > 0 ? ctx->hoist_chunk : 16;
+				const long long tiles_per_frame = (long long)cdiv(wf, FT_W) * cdiv(hf, FT_H);
+				while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
+				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
+				if (!ctx->hoist_attr) {
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+					ctx->hoist_attr = true;
+				}
+				if (p->fmt == VP_FMT_RGGB8)
+					k_reproject_hoist<FMT_RGGB><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				else
+					k_reproject_hoist<FMT_GRBG><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				rc = check_launch(ctx, "k_reproject_hoist");
+			} else if (staged) {
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), g);
 				if (p->fmt == VP_FMT_RGGB8)
 					k_reproject_staged<FMT_RGGB><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf);

@@ -116,6 +116,7 @@ def load() -> C.CDLL:
         "vp_ctx_stream": (vp, [vp]),
         "vp_ctx_set_group": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_lanes": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_hoist_chunk": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
@@ -335,7 +336,8 @@ class Context:
     def set_group(self, n: int):
         self._ck(self.lib.vp_ctx_set_group(self.h, n))
 
-    def set_staged_reproject(self, on: bool):
+    def set_staged_reproject(self, on):
+        """0/False = direct gather, 1/True = staged per frame, 2 = staged with the frame-invariant part hoisted (default)."""
         self._ck(self.lib.vp_ctx_set_staged_reproject(self.h, int(on)))
 
     def set_stream_circ(self, on: bool):
@@ -343,6 +345,9 @@ class Context:
 
     def set_fused_sat(self, on: bool):
         self._ck(self.lib.vp_ctx_set_fused_sat(self.h, int(on)))
+
+    def set_hoist_chunk(self, n: int):
+        self._ck(self.lib.vp_ctx_set_hoist_chunk(self.h, n))
 
     def set_lanes(self, n: int):
         self._ck(self.lib.vp_ctx_set_lanes(self.h, n))
