@@ -225,6 +225,10 @@ VP_API int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames);
 /* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
  * tiled kernel; results are bit-identical */
 VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);
+/* A/B switch (default on; needs stream_circ on and fused_sat off): circularity straight from the row prefix sums -- no
+ * column scan, no materialised summed-area table; the exactness bound of the SAT is checked after the fact and frames
+ * that leave it are redone in the reference's sequential order; results are bit-identical */
+VP_API int vp_ctx_set_sat_free(vp_ctx* ctx, int on);
 /* A/B switch (default OFF: measured 6.8 vs 5.8 us/frame on B200): gradient + summed-area table in one pass (strip-resident in shared memory, aggregate
  * look-back between strips) vs gradient+row scan followed by a column scan; results are bit-identical */
 VP_API int vp_ctx_set_fused_sat(vp_ctx* ctx, int on);

@@ -74,16 +74,16 @@ def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
     check_frame(got, 0, want)
 
 
-@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat"])
+@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat", "sat_free"])
 @pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2),
                                 dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, max_blobs=64)])
 def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
     """Every A/B switch selects a different kernel for the same stage (direct-gather vs staged vs frame-invariant-hoisted reprojection, tiled vs
-    streaming circularity, two-pass vs single-pass SAT): both settings must give the oracle's bits."""
+    streaming circularity, two-pass vs single-pass SAT, circularity from a materialised SAT vs straight from the row sums): all settings must give the oracle's bits."""
     p, raw, _ = common.make_case(**kw)
     want = port.detect(raw, p)
     setter = getattr(ctx, "set_" + switch)
-    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False)}[switch]  # default last
+    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False), "sat_free": (False, True)}[switch]  # default last
     default = values[-1]
     try:
         for value in values:
@@ -106,9 +106,10 @@ def test_sat_fallback_through_every_kernel_variant(ctx, port):
     raw = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
     want = port.detect(raw, p)
     try:
-        for stream_circ, fused_sat in [(False, False), (True, True), (False, True)]:
+        for stream_circ, fused_sat, sat_free in [(False, False, True), (True, True, True), (False, True, True), (True, False, False), (True, False, True)]:
             ctx.set_stream_circ(stream_circ)
             ctx.set_fused_sat(fused_sat)
+            ctx.set_sat_free(sat_free)
             got = ctx.detect(raw, common.to_vp(p))
             assert got["sat_fallbacks"] == 1
             common.assert_float_images_equal(got["circ"], want["circ"])
@@ -116,6 +117,7 @@ def test_sat_fallback_through_every_kernel_variant(ctx, port):
     finally:
         ctx.set_stream_circ(True)
         ctx.set_fused_sat(False)
+        ctx.set_sat_free(True)
 
 
 def test_detect_batch_of_distinct_frames(ctx, port):
@@ -182,6 +184,47 @@ def test_sat_beyond_2p24_falls_back_to_sequential_order(ctx, port):
     np.testing.assert_array_equal(got["grad"], want["grad"])
     common.assert_float_images_equal(got["circ"], want["circ"])
     check_frame(got, 0, want)
+
+
+@pytest.mark.parametrize("sat_free", [True, False])
+def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free):
+    """Frames that leave the exactness bound -- one through its row sums (wide stripes), one only through the summed-area
+    table (found after the fast pass when there is no SAT) -- between clean frames of the same batch: the flagged ones
+    are redone in sequential order, the clean ones keep the results of the fast pass."""
+    p, clean, _ = common.make_case(wq=1600, hq=48, scale_mm=4.0, n_robots=3, n_balls=3, seed=3)
+    h, w = 2 * p.hq, 2 * p.wq
+    yy, xx = np.mgrid[0:h, 0:w]
+    stripes = (((xx + yy) // 6) % 2 * 255).astype(np.uint8)
+    wide = clean.reshape(h, w).copy()
+    wide[:, :3000] = stripes[:, :3000]      # row sums beyond 2^22, blobs to the right of the stripes
+    narrow = clean.reshape(h, w).copy()
+    narrow[:, :500] = stripes[:, :500]      # row sums stay small, the SAT does not
+    frames = [clean, wide.reshape(-1), clean, narrow.reshape(-1), clean]
+    wants = [port.detect(f, p) for f in frames]
+    rs = [np.abs(np.cumsum(wt["grad"].astype(np.float64), axis=1)).max() for wt in wants]
+    assert rs[1] >= 2 ** 22 and rs[3] < 2 ** 22 <= wants[3]["max_abs_sat"] and wants[0]["max_abs_sat"] < 2 ** 21
+    vp = common.to_vp(p)
+    n, nf, rb = len(frames), p.wf * p.hf, frames[0].size
+    bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
+    ctx.set_sat_free(sat_free)
+    try:
+        ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                                bufs["m"].device_ptr, bufs["c"].device_ptr)
+        assert ctx.sat_fallbacks() == 2
+        circ = bufs["circ"].read(np.float32).reshape(n, p.hf, p.wf)
+        counter = bufs["c"].read(np.int32).reshape(n, 3)
+        m = bufs["m"].read(np.uint8).reshape(n, vp.max_blobs, 22)
+    finally:
+        ctx.set_sat_free(True)
+    for i, wt in enumerate(wants):
+        common.assert_float_images_equal(circ[i], wt["circ"])
+        np.testing.assert_array_equal(counter[i], wt["counter"])
+        k = min(int(counter[i, 0]), vp.max_blobs)
+        assert k > 0
+        common.assert_matches_equal(m[i, :k].copy().view(lib.MATCH_DTYPE).reshape(-1), wt["matches"])
+    for b in bufs.values():
+        b.release()
 
 
 def test_detect_device_pointer_api_matches_host_api(ctx, port):

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdint.h>
+#include <type_traits>
 
 #include "vp_b200.h"
 
@@ -922,8 +923,9 @@ __global__ void k_gradient_dot(const uint32_t* __restrict__ in, float* __restric
  * row sum leaves the exact range of fp32 (satHorizontal.cl:26-31 would start rounding). */
 /* gradient + exact row prefix sums of one image row by one warp; `srow` may point to global or shared memory.
  * Returns true if a row sum left the exactness bound. */
+template <class SumT>
 __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, int y, int wf, int hf, int o, int lane, float* __restrict__ grow,
-                                             int32_t* __restrict__ srow)
+                                             SumT* __restrict__ srow)
 {
 	const uint32_t* row = img + y * wf;
 	const uint32_t* up = img + min(y + o, hf - 1) * wf;
@@ -970,14 +972,17 @@ __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, i
 			bad |= (abs(s0) >= SAT_EXACT_LIMIT) | (abs(s1) >= SAT_EXACT_LIMIT) | (abs(s2) >= SAT_EXACT_LIMIT) | (abs(s3) >= SAT_EXACT_LIMIT);
 			if (vec) {
 				*reinterpret_cast<float4*>(grow + x0) = make_float4((float)g[0], (float)g[1], (float)g[2], (float)g[3]);
-				*reinterpret_cast<int4*>(srow + x0) = make_int4(s0, s1, s2, s3);
+				if constexpr (std::is_integral<SumT>::value)
+					*reinterpret_cast<int4*>(srow + x0) = make_int4(s0, s1, s2, s3);
+				else /* fp32: exact below 2^24; anything at or above SAT_EXACT_LIMIT raises the flag anyway */
+					*reinterpret_cast<float4*>(srow + x0) = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
 			} else {
 				const int s[4] = { s0, s1, s2, s3 };
 #pragma unroll
 				for (int k = 0; k < 4; k++)
 					if (x0 + k < wf) {
 						grow[x0 + k] = (float)g[k];
-						srow[x0 + k] = s[k];
+						srow[x0 + k] = (SumT)s[k];
 					}
 			}
 		}
@@ -986,8 +991,9 @@ __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, i
 }
 
 constexpr int ROWSCAN_WARPS = 8;
+template <class SumT>
 __global__ void __launch_bounds__(ROWSCAN_WARPS * 32) k_grad_rowscan(const uint32_t* __restrict__ flat, float* __restrict__ grad,
-                                                                     int32_t* __restrict__ rowsum, int wf, int hf, int o,
+                                                                     SumT* __restrict__ rowsum, int wf, int hf, int o,
                                                                      int* __restrict__ flag)
 {
 	const int lane = threadIdx.x & 31;
@@ -1534,8 +1540,10 @@ template <int R>
 __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
                                                      int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
                                                      const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                                                     uint32_t* __restrict__ masks, int wpr)
+                                                     uint32_t* __restrict__ masks, int wpr, int only_flagged)
 {
+	if (only_flagged && flag[blockIdx.z] == 0)
+		return; /* second pass of the SAT-free flow: only frames that left the exactness bound are redone here */
 	constexpr int K = R - 1, D = R + 2;
 	constexpr int LO = R + 2;          /* first output lane: needs Q from lane-(R+1) and a circularity from lane-1 */
 	constexpr int SWU = 32 - LO - 1;   /* output lanes LO..30 */
@@ -1715,6 +1723,235 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 	publish_counters(lane, counter + 3 * f, nb, ns, npk);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * SAT-free circularity (default of the fused path).
+ *
+ * satBlobCenter.cl:37-40 only ever uses the summed-area table through four box sums, and a box sum over columns
+ * (u, u+K] x rows (v, v+K] is  sum_{y in (v, v+K]} [RS(u+K, y) - RS(u, y)]  with RS the row prefix sums that
+ * k_grad_rowscan already produces.  So the column scan (satVertical.cl) and the materialised SAT are not needed: the
+ * streaming kernel keeps a K-row sliding window of horizontal box sums per lane,
+ *     hrow(t) = RS(u+K, t) - RS(u, t),     Q(u, v = t-K) = Q(u, v-1) + hrow(t) - hrow(t-K),
+ * all exact integers in fp32 inside the exactness bound -- bit-identical to the SAT form by the argument at
+ * SAT_EXACT_LIMIT.  What the SAT was also needed for is the bound itself (|SAT| < 2^22 everywhere): every lane
+ * accumulates the column sum of RS over its segment's rows and the largest magnitude the running sum reached;
+ * k_sat_check_fix combines the segments (|SAT(x,y)| <= |carry(x, seg)| + max|local|, conservative) and raises the frame's
+ * flag.  Flagged frames (never seen on camera images) are redone afterwards in the reference's sequential order
+ * (k_sat_check_fix, then k_circ_stream's literal path).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* border pixels (taps clamp at an image edge): the four clamped boxes summed row by row from RS */
+__global__ void __launch_bounds__(256) k_circ_border_rs(const float* __restrict__ rs, float* __restrict__ circ_out, int w, int h, int r,
+                                                        const int* __restrict__ flag)
+{
+	const int f = blockIdx.y;
+	if (flag[f] != 0)
+		return;
+	const int id = blockIdx.x * 256 + threadIdx.x;
+	const int rr = min(r, h / 2), rc = min(r, w / 2); /* border thickness if the image is smaller than 2r */
+	const int top = rr * w, mid_h = h - 2 * rr;
+	int x, y;
+	if (id < top) {
+		y = id / w;
+		x = id - y * w;
+	} else if (id < 2 * top) {
+		const int k = id - top;
+		y = k / w;
+		x = k - y * w;
+		y += h - rr;
+	} else {
+		const int k = id - 2 * top;
+		if (k >= mid_h * 2 * rc)
+			return;
+		y = k / (2 * rc);
+		const int c = k - y * 2 * rc;
+		y += rr;
+		x = c < rc ? c : w - 2 * rc + c;
+	}
+	const size_t fbase = (size_t)f * w * h;
+	const float* rsf = rs + fbase;
+	const int xp = clampi(x + r, 0, w - 1), x1 = clampi(x + 1, 0, w - 1);
+	const int xm = clampi(x - 1, 0, w - 1), xr = clampi(x - r, 0, w - 1);
+	const int yp = clampi(y + r, 0, h - 1), y1 = clampi(y + 1, 0, h - 1);
+	const int ym = clampi(y - 1, 0, h - 1), yr = clampi(y - r, 0, h - 1);
+	/* S(a,b) - S(a,c) - S(d,b) + S(d,c) == sum over rows (c, b] of RS(a) - RS(d)   (satBlobCenter.cl:37-40 with clamped taps) */
+	float bp_p = 0.f, bp_n = 0.f, bn_p = 0.f, bn_n = 0.f;
+	for (int row = y1 + 1; row <= yp; row++) {
+		const float* p = rsf + row * w;
+		bp_p = __fadd_rn(bp_p, __fsub_rn(__ldg(p + xp), __ldg(p + x1))); /* pp */
+		bn_p = __fadd_rn(bn_p, __fsub_rn(__ldg(p + xm), __ldg(p + xr))); /* -np */
+	}
+	for (int row = yr + 1; row <= ym; row++) {
+		const float* p = rsf + row * w;
+		bp_n = __fadd_rn(bp_n, __fsub_rn(__ldg(p + xp), __ldg(p + x1))); /* -pn */
+		bn_n = __fadd_rn(bn_n, __fsub_rn(__ldg(p + xm), __ldg(p + xr))); /* nn */
+	}
+	const float pp = bp_p, nn = bn_n, pn = __fsub_rn(0.0f, bp_n), np = __fsub_rn(0.0f, bn_p);
+	circ_out[fbase + y * w + x] = __fdiv_rn(min_cl(min_cl(pp, nn), min_cl(pn, np)), (float)(r * r));
+}
+
+template <int R>
+__global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream_rs(const float* __restrict__ rs, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
+                                                     int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
+                                                     const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                                                     uint32_t* __restrict__ masks, int wpr, float* __restrict__ segsum, float* __restrict__ segmax)
+{
+	constexpr int K = R - 1, D = R + 2;
+	constexpr int LO = R + 2;          /* first output lane: needs Q from lane-(R+1) and a circularity from lane-1 */
+	constexpr int SWU = 32 - LO - 1;   /* output lanes LO..30 */
+	constexpr float DIV = (float)(R * R);
+	constexpr float RCP = 1.0f / DIV;
+	const int lane = threadIdx.x & 31;
+	const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
+	const int f = blockIdx.z;
+	const int xs = strip * SWU;
+	if (xs >= w || flag[f] != 0)
+		return; /* frames whose row sums left the bound are done by the fallback pass */
+	const int x = xs + lane - LO;                       /* this lane's pixel column (may be outside the image) */
+	const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
+	const size_t fbase = (size_t)f * w * h;
+	const float* rsf = rs + fbase;
+	float* circf = circ_out + fbase;
+	const uint32_t* flatf = flat + fbase;
+	const bool x_in = x >= 0 && x < w;
+	const bool out_lane = lane >= LO && lane <= 30 && x < w; /* x >= 0 follows from lane >= LO */
+	const bool used_lane = x_in && lane >= LO - 1;            /* output lanes and their left/right neighbours inside the image */
+	int nb = 0, ns = 0, npk = 0;
+	int32_t* rcf = rowcount + f * h;
+	uint32_t* mkf = masks + (size_t)f * h * wpr;
+
+	auto publish = [&](int cls, int yy) { /* warp-uniform call */
+		if (cls == 3) {
+			atomicOr(mkf + (yy * wpr + (x >> 5)), 1u << (x & 31));
+			atomicAdd(rcf + yy, 1);
+		}
+		nb += __popc(__ballot_sync(0xffffffffu, cls == 3));
+		ns += __popc(__ballot_sync(0xffffffffu, cls == 2));
+		npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
+	};
+
+	/* RS columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
+	 * pixels would use (those read the value k_circ_border_rs computed), so u is merely kept inside the row: the u+K load
+	 * may run up to K floats past the row end, which stays inside the (padded) scratch. */
+	const int ua = clampi(x + 1, 0, w - 1);
+	const bool lane_border = !(x - R >= 0 && x + R <= w - 1);
+	const bool warp_has_border_lane = __any_sync(0xffffffffu, used_lane && lane_border);
+	const float* pa = rsf + ua;
+	float* pc = circf + (x_in ? x : 0);
+
+	float la[D], lb[D], cb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D], cbc[D];
+#pragma unroll
+	for (int i = 0; i < D; i++)
+		hn[i] = qa[i] = qb[i] = cr[i] = cb[i] = cbc[i] = 0.f;
+	float qrun = 0.f;                 /* sum of the last K hrow values */
+	float colrun = 0.f, colmax = 0.f; /* column sum of RS(ua, .) over this segment's rows, and its largest magnitude on the way */
+	const int t0 = ys - 1 - R;
+	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
+
+	auto load_group = [&](int t) {
+		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: no row of the group is clamped */
+			const float* p = elem_ptr(pa, (unsigned)(t * w));
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				la[s] = __ldg(p);
+				lb[s] = __ldg(p + K);
+				p += w;
+			}
+		} else {
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
+				la[s] = __ldg(p);
+				lb[s] = __ldg(p + K);
+			}
+		}
+		const int y0 = t - R; /* circularity rows of the group: y0 .. y0+D-1 */
+		if (warp_has_border_lane || y0 < R || y0 + D - 1 > h - 1 - R) { /* warp-uniform */
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				const int y = y0 + s;
+				if (used_lane && y >= 0 && y < h && (lane_border || y < R || y > h - 1 - R))
+					cb[s] = __ldcg(elem_ptr(pc, (unsigned)(y * w)));
+			}
+		}
+	};
+
+	load_group(t0);
+	for (int g = 0; g < n_groups; g++) {
+		const int t = t0 + g * D;
+#pragma unroll
+		for (int i = 0; i < K; i++)
+			hold[i] = hn[D - K + i];
+#pragma unroll
+		for (int s = 0; s < D; s++) {
+			hn[s] = __fsub_rn(lb[s], la[s]); /* hrow(t+s) */
+			cbc[s] = cb[s];
+			if (t + s >= ys && t + s < ye) { /* warp-uniform: rows this segment owns */
+				colrun = __fadd_rn(colrun, la[s]);
+				colmax = fmaxf(colmax, fabsf(colrun));
+			}
+		}
+		if (g + 1 < n_groups)
+			load_group(t + D);
+
+		constexpr int DD = 4 * D;
+		const int y0 = t - R; /* circularity row of step 0 */
+		float crow[D + 2]; /* circularity rows y0-2 .. y0+D-1 */
+		crow[0] = cr[(0 - R - 2 + DD) % D];
+		crow[1] = cr[(0 - R - 1 + DD) % D];
+#pragma unroll
+		for (int s = 0; s < D; s++) {
+			const int so = (s - K + DD) % D, sq = (s - 2 * R + DD) % D, sc = (s - R + DD) % D;
+			const float h_old = s - K >= 0 ? hn[s - K >= 0 ? s - K : 0] : hold[s - K >= 0 ? 0 : s];
+			qrun = __fadd_rn(qrun, __fsub_rn(hn[s], h_old)); /* Q row v = t+s-K: rows v+1 .. v+K */
+			const float q = qrun;
+			qa[so] = q;
+			qb[so] = __shfl_up_sync(0xffffffffu, q, R + 1);
+			const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
+			const float q0 = __fmul_rn(m, RCP);
+			float c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0); /* == m / (R*R), satBlobCenter.cl:41 */
+			const int y = y0 + s;
+			if (lane_border || y < R || y > h - 1 - R)
+				c = cbc[s]; /* border pixel: the value k_circ_border_rs computed */
+			cr[sc] = c;
+			crow[s + 2] = c;
+			if (out_lane && y >= ys && y < ye)
+				*elem_ptr(pc, (unsigned)(y * w)) = c;
+		}
+		float mx = crow[1];
+#pragma unroll
+		for (int s = 2; s <= D; s++)
+			mx = fmaxf(mx, crow[s]);
+		if (__any_sync(0xffffffffu, out_lane && !(mx < thr))) {
+#pragma unroll 1
+			for (int i = 1; i <= D; i++) {
+				const int yy = y0 + i - 2;
+				float cm = crow[1], up = crow[0], dn = crow[2];
+#pragma unroll
+				for (int k = 2; k <= D; k++)
+					if (i == k) {
+						cm = crow[k];
+						up = crow[k - 1];
+						dn = crow[k + 1];
+					}
+				const bool cand = out_lane && yy >= ys && yy < ye && !(cm < thr);
+				if (!__any_sync(0xffffffffu, cand))
+					continue;
+				const float cl = __shfl_up_sync(0xffffffffu, cm, 1), crr = __shfl_down_sync(0xffffffffu, cm, 1);
+				const int cls = cand ? classify_px(flatf, w, h, x, yy, radius, thr, min_score, need_score, cm, x > 0 ? cl : cm, x < w - 1 ? crr : cm,
+				                                   yy > 0 ? up : cm, yy < h - 1 ? dn : cm)
+				                     : 0;
+				publish(cls, yy);
+			}
+		}
+	}
+	publish_counters(lane, counter + 3 * f, nb, ns, npk);
+	if (x + 1 >= 0 && x + 1 <= w - 1) { /* column ua is really this lane's (not a clamped duplicate) */
+		const size_t i = ((size_t)f * gridDim.y + blockIdx.y) * w + ua;
+		segsum[i] = colrun;
+		segmax[i] = colmax;
+	}
+}
+
 __device__ __forceinline__ void store_match(uint8_t* __restrict__ dst, float mx, float my, const uint32_t color[3], uint32_t center, float circ,
                                             float score)
 {
@@ -1730,28 +1967,36 @@ __device__ __forceinline__ void store_match(uint8_t* __restrict__ dst, float mx,
 	d[9] = (uint16_t)us; d[10] = (uint16_t)(us >> 16);
 }
 
-/* disc statistics of one blob computed by the whole warp: lane = dx, loop over dy (blobList.cl:63-72) */
+/* disc statistics of one blob computed by the whole warp (blobList.cl:63-72): the (2r+1)^2 window is dealt out to the
+ * lanes position by position, four independent loads in flight per lane; integer sums, so the order is irrelevant */
 __device__ __forceinline__ DiscStats disc_stats_warp(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, int lane)
 {
 	DiscStats d;
 	d.n = 0;
 	d.s1[0] = d.s1[1] = d.s1[2] = d.s2[0] = d.s2[1] = d.s2[2] = 0;
-	const int sq = radius * radius;
-	for (int dx0 = -radius; dx0 <= radius; dx0 += 32) {
-		const int dx = dx0 + lane;
-		if (dx <= radius) {
-			const int xx = clampi(x + dx, 0, w - 1);
-			for (int dy = -radius; dy <= radius; dy++)
-				if (dx * dx + dy * dy <= sq) {
-					const uint32_t v = __ldg(img + (size_t)clampi(y + dy, 0, h - 1) * w + xx);
+	const int sq = radius * radius, side = 2 * radius + 1, area = side * side;
+	for (int i0 = 0; i0 < area; i0 += 128) {
+		uint32_t v[4];
+		bool in[4];
 #pragma unroll
-					for (int k = 0; k < 3; k++) {
-						const uint32_t c = (v >> (8 * k)) & 255u;
-						d.s1[k] += c;
-						d.s2[k] += c * c;
-					}
-					d.n++;
+		for (int k = 0; k < 4; k++) {
+			const int i = i0 + 32 * k + lane;
+			const int row = i / side;
+			const int dy = row - radius, dx = i - row * side - radius;
+			in[k] = i < area && dx * dx + dy * dy <= sq;
+			v[k] = in[k] ? __ldg(img + (size_t)clampi(y + dy, 0, h - 1) * w + clampi(x + dx, 0, w - 1)) : 0u;
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (in[k]) {
+#pragma unroll
+				for (int c = 0; c < 3; c++) {
+					const uint32_t cc = (v[k] >> (8 * c)) & 255u;
+					d.s1[c] += cc;
+					d.s2[c] += cc * cc;
 				}
+				d.n++;
+			}
 		}
 	}
 #pragma unroll
@@ -1770,17 +2015,19 @@ __device__ __forceinline__ DiscStats disc_stats_warp(const uint32_t* __restrict_
 __device__ __forceinline__ void emit_match(const uint32_t* __restrict__ im, const float* __restrict__ ci, int w, int h, int x, int y, int radius,
                                            uint8_t* __restrict__ dst, int lane)
 {
-	const DiscStats d = disc_stats_warp(im, w, h, x, y, radius, lane);
-	if (lane != 0)
-		return;
+	/* requested before the disc statistics so that their latency overlaps (every lane loads; lane 0 uses them) */
 	const float c = __ldg(ci + (size_t)y * w + x);
 	const float cnx = __ldg(ci + (size_t)y * w + max(x - 1, 0)), cpx = __ldg(ci + (size_t)y * w + min(x + 1, w - 1));
 	const float cny = __ldg(ci + (size_t)max(y - 1, 0) * w + x), cpy = __ldg(ci + (size_t)min(y + 1, h - 1) * w + x);
+	const uint32_t centre = __ldg(im + (size_t)y * w + x);
+	const DiscStats d = disc_stats_warp(im, w, h, x, y, radius, lane);
+	if (lane != 0)
+		return;
 	const float score = blob_score(d, c);
 	const float mx = __fadd_rn((float)x, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cnx, cpx)), __fadd_rn(__fsub_rn(cnx, __fmul_rn(2.0f, c)), cpx))); /* :93 */
 	const float my = __fadd_rn((float)y, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(cny, cpy)), __fadd_rn(__fsub_rn(cny, __fmul_rn(2.0f, c)), cpy))); /* :94 */
 	const uint32_t color[3] = { d.s1[0] / (uint32_t)d.n, d.s1[1] / (uint32_t)d.n, d.s1[2] / (uint32_t)d.n }; /* :85 */
-	store_match(dst, mx, my, color, __ldg(im + (size_t)y * w + x), c, score);
+	store_match(dst, mx, my, color, centre, c, score);
 }
 
 /* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp */

@@ -80,6 +80,10 @@ struct vp_ctx {
 	int hoist_chunk = 0;      /* frames per CTA of the hoisted kernel; 0 = automatic */
 	int sm_count = 148;
 	bool stream_circ = true;
+	bool sat_free = true; /* circularity straight from the row sums: no column scan, no materialised SAT (needs stream_circ, !fused_sat) */
+	float* segsum[MAX_LANES] = {}; /* per lane: column sums of the row sums per (frame of the group, row segment) */
+	float* segmax[MAX_LANES] = {};
+	size_t seg_words = 0;
 	bool fused_sat = false; /* measured slower than row scan + column scan on B200 (profiles/r01_fused_sat_sweep.txt); kept as an A/B option */
 	bool grad_sat_attr = false;
 	bool hoist_attr = false;
@@ -332,7 +336,7 @@ int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames, siz
 		}
 		ctx->scratch_px = 0;
 		for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
-			CK(ctx, cudaMalloc(&ctx->rowsum[l], group_px * 4));
+			CK(ctx, cudaMalloc(&ctx->rowsum[l], group_px * 4 + 256)); /* k_circ_stream_rs reads up to R-1 floats past a row end */
 			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4 + 256)); /* k_circ_stream reads up to R-1 floats past a row end */
 		}
 		ctx->scratch_px = group_px;
@@ -393,13 +397,9 @@ int launch_blob_list(vp_ctx* ctx, const uint32_t* flat, const float* circ, int w
 	return launch_peaks_emit(ctx, ctx->stream, flat, circ, w, h, n, radius, max_matches, first_slot, rowcount, masks, matches, match_stride);
 }
 
-/* single-launch fallback: recompute the SAT of flagged frames in the reference's sequential order */
-__global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
-                                                  const int* __restrict__ flag)
+/* recompute the SAT of one frame in the reference's sequential order (one CTA of 1024 threads) */
+__device__ __forceinline__ void sat_fix_frame(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h, size_t fbase)
 {
-	if (flag[blockIdx.x] == 0)
-		return;
-	const size_t fbase = (size_t)blockIdx.x * w * h;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	for (int y = warp; y < h; y += 32) { /* satHorizontal.cl:26-31 */
 		const size_t base = fbase + (size_t)y * w;
@@ -426,6 +426,51 @@ __global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad
 			sat[fbase + (size_t)y * w + x] = sum;
 		}
 	}
+}
+
+/* single-launch fallback: recompute the SAT of flagged frames in the reference's sequential order */
+__global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
+                                                  const int* __restrict__ flag)
+{
+	if (flag[blockIdx.x] == 0)
+		return;
+	sat_fix_frame(grad, hor, sat, w, h, (size_t)blockIdx.x * w * h);
+}
+
+/* SAT-free flow, after the fast pass, one CTA per frame: (1) the exactness bound of the summed-area table from the
+ * per-segment column sums, |SAT(x, y)| <= |sum of the segments above| + max |running sum inside the segment|
+ * (conservative); (2) for a frame that left the bound -- here or already in the row scan -- forget what the fast pass
+ * published and (3) build the SAT in the reference's sequential order for k_circ_stream's literal path. */
+__global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict__ segsum, const float* __restrict__ segmax, int n_seg,
+                                                        const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
+                                                        int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                                                        uint32_t* __restrict__ masks, int wpr)
+{
+	const int f = blockIdx.x;
+	int state = flag[f];
+	if (state == 0) {
+		bool bad = false;
+		for (int x = threadIdx.x; x < w; x += 1024) {
+			const float* ss = segsum + (size_t)f * n_seg * w + x;
+			const float* sm = segmax + (size_t)f * n_seg * w + x;
+			float carry = 0.f;
+			for (int k = 0; k < n_seg; k++) {
+				bad |= !(__fadd_rn(fabsf(carry), sm[k * w]) < (float)SAT_EXACT_LIMIT);
+				carry = __fadd_rn(carry, ss[k * w]);
+			}
+		}
+		if (!__syncthreads_or(bad))
+			return;
+		if (threadIdx.x == 0)
+			flag[f] = 2;
+	}
+	for (int i = threadIdx.x; i < h * wpr; i += 1024)
+		masks[(size_t)f * h * wpr + i] = 0u;
+	for (int i = threadIdx.x; i < h; i += 1024)
+		rowcount[(size_t)f * h + i] = 0;
+	if (threadIdx.x < 3)
+		counter[3 * f + threadIdx.x] = 0;
+	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
 }
 
 int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
@@ -559,6 +604,8 @@ void vp_ctx_destroy(vp_ctx* c)
 	for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
 		cudaFree(c->rowsum[l]);
 		cudaFree(c->sat[l]);
+		cudaFree(c->segsum[l]);
+		cudaFree(c->segmax[l]);
 		if (l > 0 && c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
 		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
 	}
@@ -598,6 +645,13 @@ int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memor
 	REQUIRE(ctx, ctx, "ctx is null");
 	REQUIRE(ctx, on >= 0 && on <= 2, "variant must be 0 (direct), 1 (staged) or 2 (staged, frame-invariant part hoisted)");
 	ctx->staged_reproject = on;
+	return VP_OK;
+}
+
+int vp_ctx_set_sat_free(vp_ctx* ctx, int on) /* A/B switch: circularity from the row sums (no column scan, no SAT) vs from a materialised SAT */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->sat_free = on != 0;
 	return VP_OK;
 }
 
@@ -1102,6 +1156,27 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
+	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
+	const int seg = seg_env > 0 ? seg_env : 128; /* rows per CTA of the streaming circularity kernels */
+	const int n_seg = cdiv(hf, seg);
+	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
+	if (sat_free) {
+		const size_t need = (size_t)G * n_seg * wf;
+		if (need > ctx->seg_words) {
+			CK(ctx, cudaDeviceSynchronize());
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+				cudaFree(ctx->segsum[l]);
+				cudaFree(ctx->segmax[l]);
+				ctx->segsum[l] = ctx->segmax[l] = nullptr;
+			}
+			ctx->seg_words = 0;
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+				CK(ctx, cudaMalloc(&ctx->segsum[l], need * 4));
+				CK(ctx, cudaMalloc(&ctx->segmax[l], need * 4));
+			}
+			ctx->seg_words = need;
+		}
+	}
 	/* single-pass gradient + SAT: a strip of srows rows x full width lives in shared memory */
 	int srows = (int)((200u * 1024u) / ((size_t)wf * 4));
 	if (srows > 32) srows = 32;
@@ -1178,15 +1253,17 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 				const long long tiles_per_frame = (long long)cdiv(wf, FT_W) * cdiv(hf, FT_H);
 				while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
+				static const size_t hoist_pad = getenv("VP_HOIST_PAD") ? (size_t)atoi(getenv("VP_HOIST_PAD")) : 0; /* tuning aid: caps residency */
+				const size_t HOIST_SMEM_L = HOIST_SMEM + hoist_pad;
 				if (!ctx->hoist_attr) {
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
 					ctx->hoist_attr = true;
 				}
 				if (p->fmt == VP_FMT_RGGB8)
-					k_reproject_hoist<FMT_RGGB><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+					k_reproject_hoist<FMT_RGGB><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 				else
-					k_reproject_hoist<FMT_GRBG><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+					k_reproject_hoist<FMT_GRBG><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 				rc = check_launch(ctx, "k_reproject_hoist");
 			} else if (staged) {
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), g);
@@ -1204,7 +1281,11 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 			}
 			if (rc) return rc;
 		}
-		if (fused_sat) {
+		if (sat_free) {
+			Stage st(ctx, "grad_rowscan", 1, s);
+			k_grad_rowscan<float><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
+			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
+		} else if (fused_sat) {
 			Stage st(ctx, "grad_sat", 1, s);
 			int* ticket = ctx->sync_words + f0;
 			int* ready = ctx->sync_words + n_frames + (size_t)f0 * n_strips;
@@ -1214,7 +1295,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		} else {
 			{
 				Stage st(ctx, "grad_rowscan", 1, s);
-				k_grad_rowscan<<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
+				k_grad_rowscan<int32_t><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
 				if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
 			}
 			{
@@ -1222,16 +1303,55 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 				if ((rc = launch_colscan(ctx, s, rowsum, sat, wf, hf, g, flag))) return rc;
 			}
 		}
-		{
+		if (!sat_free) {
 			Stage st(ctx, "sat_fix", 1, s);
 			k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag);
 			if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
 		}
-		if (fused_circ) {
+		if (sat_free) {
+			const int r = p->circle_radius;
+			float* segsum = ctx->segsum[lane];
+			float* segmax = ctx->segmax[lane];
+			{
+				Stage st(ctx, "circ_peaks", 2, s);
+				const int rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
+				const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
+				if (n_border > 0)
+					k_circ_border_rs<<<dim3(cdiv(n_border, 256), g), 256, 0, s>>>((const float*)rowsum, circ, wf, hf, r, flag);
+#define VP_CSR(RR)                                                                                                             \
+	case RR: {                                                                                                                 \
+		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
+		k_circ_stream_rs<RR><<<grid, 128, 0, s>>>((const float*)rowsum, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, \
+		                                          counter, rowcount, masks, wpr, segsum, segmax);                              \
+	} break;
+				switch (r) {
+					VP_CSR(1) VP_CSR(2) VP_CSR(3) VP_CSR(4) VP_CSR(5) VP_CSR(6) VP_CSR(7) VP_CSR(8) VP_CSR(9) VP_CSR(10) VP_CSR(11) VP_CSR(12)
+				}
+#undef VP_CSR
+				if ((rc = check_launch(ctx, "k_circ_stream_rs"))) return rc;
+			}
+			{
+				/* the exactness bound of the summed-area table, checked after the fact; frames that left it (or whose row sums
+				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
+				Stage st(ctx, "sat_check", 2, s);
+				k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
+#define VP_CSF(RR)                                                                                                             \
+	case RR: {                                                                                                                 \
+		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
+		                                       rowcount, masks, wpr, 1);                                                       \
+	} break;
+				switch (r) {
+					VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
+				}
+#undef VP_CSF
+				if ((rc = check_launch(ctx, "sat_check/fallback"))) return rc;
+			}
+		} else if (fused_circ) {
 			Stage st(ctx, "circ_peaks", ctx->stream_circ ? 2 : 1, s);
 			if (ctx->stream_circ) {
-				static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
-				const int seg = seg_env > 0 ? seg_env : 128;
 				{
 					const int r = p->circle_radius, rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
 					const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
@@ -1243,7 +1363,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
 		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, seg), g);                                                             \
 		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
-		                                       rowcount, masks, wpr);                                                          \
+		                                       rowcount, masks, wpr, 0);                                                       \
 	} break;
 				switch (p->circle_radius) {
 					VP_CS(1) VP_CS(2) VP_CS(3) VP_CS(4) VP_CS(5) VP_CS(6) VP_CS(7) VP_CS(8) VP_CS(9) VP_CS(10) VP_CS(11) VP_CS(12)

@@ -117,6 +117,7 @@ def load() -> C.CDLL:
         "vp_ctx_set_group": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_lanes": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_hoist_chunk": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_sat_free": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
@@ -345,6 +346,9 @@ class Context:
 
     def set_fused_sat(self, on: bool):
         self._ck(self.lib.vp_ctx_set_fused_sat(self.h, int(on)))
+
+    def set_sat_free(self, on: bool):
+        self._ck(self.lib.vp_ctx_set_sat_free(self.h, int(on)))
 
     def set_hoist_chunk(self, n: int):
         self._ck(self.lib.vp_ctx_set_hoist_chunk(self.h, n))
