@@ -1724,7 +1724,7 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 }
 
 /* ------------------------------------------------------------------------------------------------
- * SAT-free circularity (default of the fused path).
+ * SAT-free circularity (default of the fused path); no separate border pass.
  *
  * satBlobCenter.cl:37-40 only ever uses the summed-area table through four box sums, and a box sum over columns
  * (u, u+K] x rows (v, v+K] is  sum_{y in (v, v+K]} [RS(u+K, y) - RS(u, y)]  with RS the row prefix sums that
@@ -1738,56 +1738,6 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
  * flag.  Flagged frames (never seen on camera images) are redone afterwards in the reference's sequential order
  * (k_sat_check_fix, then k_circ_stream's literal path).
  * ---------------------------------------------------------------------------------------------- */
-
-/* border pixels (taps clamp at an image edge): the four clamped boxes summed row by row from RS */
-__global__ void __launch_bounds__(256) k_circ_border_rs(const float* __restrict__ rs, float* __restrict__ circ_out, int w, int h, int r,
-                                                        const int* __restrict__ flag)
-{
-	const int f = blockIdx.y;
-	if (flag[f] != 0)
-		return;
-	const int id = blockIdx.x * 256 + threadIdx.x;
-	const int rr = min(r, h / 2), rc = min(r, w / 2); /* border thickness if the image is smaller than 2r */
-	const int top = rr * w, mid_h = h - 2 * rr;
-	int x, y;
-	if (id < top) {
-		y = id / w;
-		x = id - y * w;
-	} else if (id < 2 * top) {
-		const int k = id - top;
-		y = k / w;
-		x = k - y * w;
-		y += h - rr;
-	} else {
-		const int k = id - 2 * top;
-		if (k >= mid_h * 2 * rc)
-			return;
-		y = k / (2 * rc);
-		const int c = k - y * 2 * rc;
-		y += rr;
-		x = c < rc ? c : w - 2 * rc + c;
-	}
-	const size_t fbase = (size_t)f * w * h;
-	const float* rsf = rs + fbase;
-	const int xp = clampi(x + r, 0, w - 1), x1 = clampi(x + 1, 0, w - 1);
-	const int xm = clampi(x - 1, 0, w - 1), xr = clampi(x - r, 0, w - 1);
-	const int yp = clampi(y + r, 0, h - 1), y1 = clampi(y + 1, 0, h - 1);
-	const int ym = clampi(y - 1, 0, h - 1), yr = clampi(y - r, 0, h - 1);
-	/* S(a,b) - S(a,c) - S(d,b) + S(d,c) == sum over rows (c, b] of RS(a) - RS(d)   (satBlobCenter.cl:37-40 with clamped taps) */
-	float bp_p = 0.f, bp_n = 0.f, bn_p = 0.f, bn_n = 0.f;
-	for (int row = y1 + 1; row <= yp; row++) {
-		const float* p = rsf + row * w;
-		bp_p = __fadd_rn(bp_p, __fsub_rn(__ldg(p + xp), __ldg(p + x1))); /* pp */
-		bn_p = __fadd_rn(bn_p, __fsub_rn(__ldg(p + xm), __ldg(p + xr))); /* -np */
-	}
-	for (int row = yr + 1; row <= ym; row++) {
-		const float* p = rsf + row * w;
-		bp_n = __fadd_rn(bp_n, __fsub_rn(__ldg(p + xp), __ldg(p + x1))); /* -pn */
-		bn_n = __fadd_rn(bn_n, __fsub_rn(__ldg(p + xm), __ldg(p + xr))); /* nn */
-	}
-	const float pp = bp_p, nn = bn_n, pn = __fsub_rn(0.0f, bp_n), np = __fsub_rn(0.0f, bn_p);
-	circ_out[fbase + y * w + x] = __fdiv_rn(min_cl(min_cl(pp, nn), min_cl(pn, np)), (float)(r * r));
-}
 
 template <int R>
 __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream_rs(const float* __restrict__ rs, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
@@ -1814,7 +1764,6 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 	const uint32_t* flatf = flat + fbase;
 	const bool x_in = x >= 0 && x < w;
 	const bool out_lane = lane >= LO && lane <= 30 && x < w; /* x >= 0 follows from lane >= LO */
-	const bool used_lane = x_in && lane >= LO - 1;            /* output lanes and their left/right neighbours inside the image */
 	int nb = 0, ns = 0, npk = 0;
 	int32_t* rcf = rowcount + f * h;
 	uint32_t* mkf = masks + (size_t)f * h * wpr;
@@ -1829,31 +1778,31 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 		npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
 	};
 
-	/* RS columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
-	 * pixels would use (those read the value k_circ_border_rs computed), so u is merely kept inside the row: the u+K load
-	 * may run up to K floats past the row end, which stays inside the (padded) scratch. */
-	const int ua = clampi(x + 1, 0, w - 1);
-	const bool lane_border = !(x - R >= 0 && x + R <= w - 1);
-	const bool warp_has_border_lane = __any_sync(0xffffffffu, used_lane && lane_border);
+	/* Columns of this lane's box: (u, u+K] with u = x+1, both CLAMPED into the row.  With clamped taps the reference's
+	 * S(a,b) - S(a,c) - S(d,b) + S(d,c) is still the sum over rows (c, b] of RS(a) - RS(d), so image borders need no special
+	 * case: a clamped column pair just gives a narrower (or empty) box, and rows outside [1, h-1] contribute nothing
+	 * (clamp(y-r) = 0 starts the box at row 1; clamp(y+r) = h-1 ends it at row h-1). */
+	const int ua = clampi(x + 1, 0, w - 1), ub = clampi(x + 1 + K, 0, w - 1);
 	const float* pa = rsf + ua;
+	const int dab = ub - ua;
 	float* pc = circf + (x_in ? x : 0);
 
-	float la[D], lb[D], cb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D], cbc[D];
+	float la[D], lb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D];
 #pragma unroll
 	for (int i = 0; i < D; i++)
-		hn[i] = qa[i] = qb[i] = cr[i] = cb[i] = cbc[i] = 0.f;
+		hn[i] = qa[i] = qb[i] = cr[i] = 0.f;
 	float qrun = 0.f;                 /* sum of the last K hrow values */
 	float colrun = 0.f, colmax = 0.f; /* column sum of RS(ua, .) over this segment's rows, and its largest magnitude on the way */
 	const int t0 = ys - 1 - R;
 	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
 
 	auto load_group = [&](int t) {
-		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: no row of the group is clamped */
+		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: every row of the group is inside the image */
 			const float* p = elem_ptr(pa, (unsigned)(t * w));
 #pragma unroll
 			for (int s = 0; s < D; s++) {
 				la[s] = __ldg(p);
-				lb[s] = __ldg(p + K);
+				lb[s] = __ldg(p + dab);
 				p += w;
 			}
 		} else {
@@ -1861,16 +1810,7 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 			for (int s = 0; s < D; s++) {
 				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
 				la[s] = __ldg(p);
-				lb[s] = __ldg(p + K);
-			}
-		}
-		const int y0 = t - R; /* circularity rows of the group: y0 .. y0+D-1 */
-		if (warp_has_border_lane || y0 < R || y0 + D - 1 > h - 1 - R) { /* warp-uniform */
-#pragma unroll
-			for (int s = 0; s < D; s++) {
-				const int y = y0 + s;
-				if (used_lane && y >= 0 && y < h && (lane_border || y < R || y > h - 1 - R))
-					cb[s] = __ldcg(elem_ptr(pc, (unsigned)(y * w)));
+				lb[s] = __ldg(p + dab);
 			}
 		}
 	};
@@ -1881,10 +1821,12 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 #pragma unroll
 		for (int i = 0; i < K; i++)
 			hold[i] = hn[D - K + i];
+		const bool inner = t >= 1 && t + D - 1 <= h - 1; /* warp-uniform: no row of the group is 0 or outside the image */
 #pragma unroll
 		for (int s = 0; s < D; s++) {
 			hn[s] = __fsub_rn(lb[s], la[s]); /* hrow(t+s) */
-			cbc[s] = cb[s];
+			if (!inner && (t + s < 1 || t + s > h - 1))
+				hn[s] = 0.f;
 			if (t + s >= ys && t + s < ye) { /* warp-uniform: rows this segment owns */
 				colrun = __fadd_rn(colrun, la[s]);
 				colmax = fmaxf(colmax, fabsf(colrun));
@@ -1908,10 +1850,8 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 			qb[so] = __shfl_up_sync(0xffffffffu, q, R + 1);
 			const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
 			const float q0 = __fmul_rn(m, RCP);
-			float c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0); /* == m / (R*R), satBlobCenter.cl:41 */
+			const float c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0); /* == m / (R*R), satBlobCenter.cl:41 */
 			const int y = y0 + s;
-			if (lane_border || y < R || y > h - 1 - R)
-				c = cbc[s]; /* border pixel: the value k_circ_border_rs computed */
 			cr[sc] = c;
 			crow[s + 2] = c;
 			if (out_lane && y >= ys && y < ye)

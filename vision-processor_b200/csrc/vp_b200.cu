@@ -1313,11 +1313,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 			float* segsum = ctx->segsum[lane];
 			float* segmax = ctx->segmax[lane];
 			{
-				Stage st(ctx, "circ_peaks", 2, s);
-				const int rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
-				const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
-				if (n_border > 0)
-					k_circ_border_rs<<<dim3(cdiv(n_border, 256), g), 256, 0, s>>>((const float*)rowsum, circ, wf, hf, r, flag);
+				Stage st(ctx, "circ_peaks", 1, s);
 #define VP_CSR(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
