@@ -1784,7 +1784,8 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 	 * (clamp(y-r) = 0 starts the box at row 1; clamp(y+r) = h-1 ends it at row h-1). */
 	const int ua = clampi(x + 1, 0, w - 1), ub = clampi(x + 1 + K, 0, w - 1);
 	const float* pa = rsf + ua;
-	const int dab = ub - ua;
+	const float* pb = rsf + ub;
+	const bool box_full = __all_sync(0xffffffffu, ub - ua == K); /* false only for the strips at the left/right image edge */
 	float* pc = circf + (x_in ? x : 0);
 
 	float la[D], lb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D];
@@ -1796,38 +1797,48 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 	const int t0 = ys - 1 - R;
 	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
 
+	/* D rows of RS in flight per lane.  Rows 1..h-1 give hrow = RS(ub) - RS(ua); for every other row both loads read the
+	 * SAME address, so hrow comes out as exactly zero without a select in the consumer. */
 	auto load_group = [&](int t) {
-		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: every row of the group is inside the image */
-			const float* p = elem_ptr(pa, (unsigned)(t * w));
+		if (t >= 1 && t + D - 1 <= h - 1 && box_full) { /* warp-uniform: every row counts and no lane's columns are clamped */
 #pragma unroll
 			for (int s = 0; s < D; s++) {
-				la[s] = __ldg(p);
-				lb[s] = __ldg(p + dab);
-				p += w;
+				const float* q = elem_ptr(pa, (unsigned)((t + s) * w));
+				la[s] = __ldg(q);
+				lb[s] = __ldg(q + K); /* one address per row, the second load at an immediate offset */
+			}
+		} else if (t >= 1 && t + D - 1 <= h - 1) {
+#pragma unroll
+			for (int s = 0; s < D; s++) {
+				const unsigned o = (unsigned)((t + s) * w);
+				la[s] = __ldg(elem_ptr(pa, o));
+				lb[s] = __ldg(elem_ptr(pb, o));
 			}
 		} else {
 #pragma unroll
 			for (int s = 0; s < D; s++) {
-				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
-				la[s] = __ldg(p);
-				lb[s] = __ldg(p + dab);
+				const int row = t + s;
+				const unsigned o = (unsigned)(clampi(row, 0, h - 1) * w);
+				la[s] = __ldg(elem_ptr(pa, o));
+				lb[s] = __ldg(elem_ptr(row >= 1 && row <= h - 1 ? pb : pa, o));
 			}
 		}
 	};
 
-	load_group(t0);
-	for (int g = 0; g < n_groups; g++) {
+	/* One group = D rows, straight-line code: the shuffles and the short dependent chains of different rows overlap; ONE
+	 * vote per group decides whether any pixel reaches the threshold at all (almost never), and only then are the rows
+	 * classified one by one.  INNER groups (every row of the group is owned by the segment, both as a summed row and as an
+	 * output row) carry no per-row range predicates. */
+	auto group = [&](auto INNER_C, int g) {
+		constexpr bool INNER = decltype(INNER_C)::value;
 		const int t = t0 + g * D;
 #pragma unroll
 		for (int i = 0; i < K; i++)
 			hold[i] = hn[D - K + i];
-		const bool inner = t >= 1 && t + D - 1 <= h - 1; /* warp-uniform: no row of the group is 0 or outside the image */
 #pragma unroll
 		for (int s = 0; s < D; s++) {
 			hn[s] = __fsub_rn(lb[s], la[s]); /* hrow(t+s) */
-			if (!inner && (t + s < 1 || t + s > h - 1))
-				hn[s] = 0.f;
-			if (t + s >= ys && t + s < ye) { /* warp-uniform: rows this segment owns */
+			if (INNER || (t + s >= ys && t + s < ye)) { /* rows this segment owns */
 				colrun = __fadd_rn(colrun, la[s]);
 				colmax = fmaxf(colmax, fabsf(colrun));
 			}
@@ -1854,9 +1865,10 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 			const int y = y0 + s;
 			cr[sc] = c;
 			crow[s + 2] = c;
-			if (out_lane && y >= ys && y < ye)
+			if (out_lane && (INNER || (y >= ys && y < ye)))
 				*elem_ptr(pc, (unsigned)(y * w)) = c;
 		}
+		/* rows classified by this group: yy = y0-1 .. y0+D-2, i.e. crow[1 .. D] */
 		float mx = crow[1];
 #pragma unroll
 		for (int s = 2; s <= D; s++)
@@ -1883,6 +1895,17 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 				publish(cls, yy);
 			}
 		}
+	};
+
+	load_group(t0);
+#pragma unroll 1
+	for (int g = 0; g < n_groups; g++) {
+		const int t = t0 + g * D;
+		/* summed rows t .. t+D-1 and output rows t-R .. t-R+D-1 all inside [ys, ye) */
+		if (t - R >= ys && t + D <= ye)
+			group(IntC<1>{}, g);
+		else
+			group(IntC<0>{}, g);
 	}
 	publish_counters(lane, counter + 3 * f, nb, ns, npk);
 	if (x + 1 >= 0 && x + 1 <= w - 1) { /* column ua is really this lane's (not a clamped duplicate) */
