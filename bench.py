@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the B200-native vision-processor detection path.
 
 Metric (BASELINE.json): 2448x2048 BayerRG8 frames/s, full detection pipeline
-(demosaic -> reproject -> gradientDot -> SAT -> circularity -> blob list), aggregate over N GPUs.
+(demosaic -> reproject -> gradientDot -> row sums -> circularity -> blob list), aggregate over N GPUs.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
 
@@ -56,10 +56,10 @@ def algorithmic_bytes(lp, blobs_per_frame: float) -> dict:
     return {
         "frame": 4 * nq + 4 * nf + 4 * nf + 4 * nf + 22 * blobs_per_frame + 12,
         "reproject": 4 * nq + 4 * nf,          # raw in, flat out
-        "grad_sat": 4 * nf + 8 * nf,           # flat in, gradDot + SAT out (single pass)
-        "grad_rowscan": 4 * nf + 8 * nf,       # (two-pass alternative) flat in, gradDot + row sums out
-        "colscan": 8 * nf,                     # row sums in, SAT out
-        "circ_peaks": 8 * nf,                  # SAT in, blobCenter out (+ blob bit masks)
+        "grad_sat": 4 * nf + 8 * nf,           # (single-pass alternative) flat in, gradDot + SAT out
+        "grad_rowscan": 4 * nf + 8 * nf,       # flat in, gradDot + row prefix sums out
+        "colscan": 8 * nf,                     # (SAT-based alternative) row sums in, SAT out
+        "circ_peaks": 8 * nf,                  # row sums (or SAT) in, blobCenter out (+ blob bit masks)
         "peaks_emit": 22 * blobs_per_frame,    # sparse: records out
     }
 
@@ -288,11 +288,13 @@ def main():
     frames_per_launch = B * n_prof_steps / per_stage[top][1]  # frames of the profiled pass / launches of that kernel
     avg_ms = per_stage[top][0] / per_stage[top][1]
     achieved = abytes[top] * frames_per_launch / (avg_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per frame of each kernel from the ncu --set full capture of round 1
-    # (profiles/r01_ncu_summary.txt, 16-frame launches), scaled to the frames one launch of this run processes
-    ncu_dram_bytes_per_frame = {"reproject": (90.963200e6 + 50.066688e6) / 16, "grad_rowscan": (81.103104e6 + 107.907840e6) / 16,
-                                "colscan": (80.238080e6 + 40.717056e6) / 16, "circ_peaks": (81.146368e6 + 37.956864e6) / 16}
-    traffic = ncu_dram_bytes_per_frame[top] * frames_per_launch if top in ncu_dram_bytes_per_frame else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per frame of each kernel, from the committed ncu --set full capture
+    # (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), scaled to the frames one launch of this run processes
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        traffic = ncu[top]["dram_bytes_per_frame"] * frames_per_launch if top in ncu else None
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[top] * frames_per_launch,
                 "avg_launch_ms": avg_ms, "share_of_step": per_stage[top][0] / total_ms}

@@ -923,6 +923,19 @@ __global__ void k_gradient_dot(const uint32_t* __restrict__ in, float* __restric
  * row sum leaves the exact range of fp32 (satHorizontal.cl:26-31 would start rounding). */
 /* gradient + exact row prefix sums of one image row by one warp; `srow` may point to global or shared memory.
  * Returns true if a row sum left the exactness bound. */
+/* int -> fp32 for |v| < 2^22 on the integer and FMA pipes (I2F runs on the quarter-rate conversion pipe): adding v to the
+ * bit pattern of 1.5 * 2^23 moves the float by v units in the last place, i.e. by exactly v */
+__device__ __forceinline__ float small_int_to_float(int v) { return __fsub_rn(__int_as_float(v + 0x4B400000), 12582912.0f); }
+
+/* `img` is a flat image produced by the reprojection kernels: alpha is 255 in every pixel, so the alpha terms of the four
+ * byte dot products cancel (R.U + L.D - R.D - L.U) and need not be masked off as in grad_dot_px */
+__device__ __forceinline__ int grad_dot_opaque(uint32_t R, uint32_t L, uint32_t U, uint32_t D)
+{
+	const uint32_t pos = __dp4a(L, D, __dp4a(R, U, 0u));
+	const uint32_t neg = __dp4a(L, U, __dp4a(R, D, 0u));
+	return (int)pos - (int)neg;
+}
+
 template <class SumT>
 __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, int y, int wf, int hf, int o, int lane, float* __restrict__ grow,
                                              SumT* __restrict__ srow)
@@ -931,12 +944,13 @@ __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, i
 	const uint32_t* up = img + min(y + o, hf - 1) * wf;
 	const uint32_t* dn = img + max(y - o, 0) * wf;
 	const bool vec = (wf & 3) == 0;
+	const bool pairs = vec && (o & 1) == 0; /* R/L taps of a lane's 4 pixels are two aligned 8-byte pairs each */
 	int carry = 0;
 	bool bad = false;
 	for (int x0 = lane * 4; x0 - lane * 4 < wf; x0 += 128) {
 		int g[4] = { 0, 0, 0, 0 };
 		if (x0 < wf) {
-			uint32_t U[4], D[4];
+			uint32_t U[4], D[4], Rr[4], Ll[4];
 			if (vec) {
 				const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(up + x0));
 				const uint4 d4 = __ldg(reinterpret_cast<const uint4*>(dn + x0));
@@ -950,12 +964,22 @@ __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, i
 					D[k] = __ldg(dn + x);
 				}
 			}
+			if (pairs && x0 - o >= 0 && x0 + 3 + o <= wf - 1) { /* no tap of these 4 pixels clamps */
+				const uint2 r0 = __ldg(reinterpret_cast<const uint2*>(row + x0 + o)), r1 = __ldg(reinterpret_cast<const uint2*>(row + x0 + o + 2));
+				const uint2 l0 = __ldg(reinterpret_cast<const uint2*>(row + x0 - o)), l1 = __ldg(reinterpret_cast<const uint2*>(row + x0 - o + 2));
+				Rr[0] = r0.x; Rr[1] = r0.y; Rr[2] = r1.x; Rr[3] = r1.y;
+				Ll[0] = l0.x; Ll[1] = l0.y; Ll[2] = l1.x; Ll[3] = l1.y;
+			} else {
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const int x = x0 + k;
-				const uint32_t R = __ldg(row + min(x + o, wf - 1)), L = __ldg(row + clampi(x - o, 0, wf - 1));
-				g[k] = x < wf ? grad_dot_px(R, L, U[k], D[k]) : 0;
+				for (int k = 0; k < 4; k++) {
+					const int x = x0 + k;
+					Rr[k] = __ldg(row + min(x + o, wf - 1));
+					Ll[k] = __ldg(row + clampi(x - o, 0, wf - 1));
+				}
 			}
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				g[k] = x0 + k < wf ? grad_dot_opaque(Rr[k], Ll[k], U[k], D[k]) : 0;
 		}
 		int p1 = g[0] + g[1], p2 = p1 + g[2], p3 = p2 + g[3];
 		int incl = p3;
@@ -969,13 +993,13 @@ __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, i
 		carry += __shfl_sync(0xffffffffu, incl, 31);
 		if (x0 < wf) {
 			const int s0 = base + g[0], s1 = base + p1, s2 = base + p2, s3 = base + p3;
-			bad |= (abs(s0) >= SAT_EXACT_LIMIT) | (abs(s1) >= SAT_EXACT_LIMIT) | (abs(s2) >= SAT_EXACT_LIMIT) | (abs(s3) >= SAT_EXACT_LIMIT);
+			bad |= max(max(abs(s0), abs(s1)), max(abs(s2), abs(s3))) >= SAT_EXACT_LIMIT;
 			if (vec) {
-				*reinterpret_cast<float4*>(grow + x0) = make_float4((float)g[0], (float)g[1], (float)g[2], (float)g[3]);
+				*reinterpret_cast<float4*>(grow + x0) = make_float4(small_int_to_float(g[0]), small_int_to_float(g[1]), small_int_to_float(g[2]), small_int_to_float(g[3]));
 				if constexpr (std::is_integral<SumT>::value)
 					*reinterpret_cast<int4*>(srow + x0) = make_int4(s0, s1, s2, s3);
-				else /* fp32: exact below 2^24; anything at or above SAT_EXACT_LIMIT raises the flag anyway */
-					*reinterpret_cast<float4*>(srow + x0) = make_float4((float)s0, (float)s1, (float)s2, (float)s3);
+				else /* fp32: exact below 2^22; anything at or above SAT_EXACT_LIMIT raises the flag and is never used */
+					*reinterpret_cast<float4*>(srow + x0) = make_float4(small_int_to_float(s0), small_int_to_float(s1), small_int_to_float(s2), small_int_to_float(s3));
 			} else {
 				const int s[4] = { s0, s1, s2, s3 };
 #pragma unroll
@@ -1845,6 +1869,11 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 		}
 		if (g + 1 < n_groups)
 			load_group(t + D);
+		if (INNER && t + 3 * D <= h) { /* pull the group after the next one into L2: its loads then see L2, not DRAM latency */
+#pragma unroll
+			for (int s = 0; s < D; s++)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(elem_ptr(pa, (unsigned)((t + 2 * D + s) * w))));
+		}
 
 		constexpr int DD = 4 * D;
 		const int y0 = t - R; /* circularity row of step 0 */
