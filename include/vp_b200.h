@@ -96,6 +96,52 @@ typedef struct {
 	int32_t sample_mode;    /* vp_sample_mode */
 } vp_params;
 
+/* ---- host-side parameter derivation (CPU only, no context needed) ----------------------------------
+ * The subset of SSL_GeometryCameraCalibration / SSL_GeometryFieldSize (ssl_vision_geometry.proto) the path reads, as plain
+ * structs so that no protobuf is needed on this side of the boundary. */
+typedef struct {
+	int32_t pixel_image_width, pixel_image_height; /* quad pixels for Bayer cameras */
+	float focal_length, principal_point_x, principal_point_y, distortion;
+	float q0, q1, q2, q3; /* field -> image orientation, (x, y, z, w) as in the protobuf */
+	float tx, ty, tz;     /* translation in the camera frame, mm */
+} vp_camera_calib;
+
+typedef struct {
+	float field_length, field_width;   /* mm */
+	float boundary_width;
+	float boundary_width_goal_line;    /* < 0: field not present (goalBoundaryWidth(), CameraModel.cpp:18-20) */
+	float ball_radius;
+} vp_field_size;
+
+/* what Perspective::geometryCheck leaves behind (src/Perspective.h:32-58) */
+typedef struct {
+	vp_camera_model model;             /* Perspective::getCLCameraModel(), after ensureSize */
+	float field_scale;                 /* mm per flat pixel */
+	float visible_field_extent[4];     /* xmin, xmax, ymin, ymax, mm */
+	int32_t reprojected_field_size[2]; /* even */
+	float min_blob_radius, max_blob_radius;
+	float min_field_scale, max_field_scale; /* what the reference only logs (Perspective.cpp:92) */
+} vp_geometry;
+
+/* CameraModel::CameraModel(const SSL_GeometryCameraCalibration&), src/CameraModel.cpp:80-88 */
+VP_API int vp_camera_model_from_calib(const vp_camera_calib* calib, vp_camera_model* out);
+/* CameraModel::ensureSize, src/CameraModel.cpp:124-135 */
+VP_API int vp_camera_model_ensure_size(vp_camera_model* model, int width, int height);
+/* CameraModel::field2image (the 10-iteration CPU twin of the kernel's projection), src/CameraModel.cpp:147-157 */
+VP_API int vp_field2image(const vp_camera_model* model, const float field[3], float image[2]);
+/* CameraModel::image2field, src/CameraModel.cpp:159-172 (NaN when the ray misses the plane) */
+VP_API int vp_image2field(const vp_camera_model* model, const float image[2], float height, float field[3]);
+/* Perspective::geometryCheck, src/Perspective.cpp:66-124: field scale, visible extent, flat size, blob radii.
+ * VP_ERR_UNSUPPORTED (with *out filled in) when the camera does not see the field. */
+VP_API int vp_geometry_check(const vp_camera_model* model, const vp_field_size* field, int width, int height, double max_bot_height,
+                             float resampling_factor, float geometry_tolerance, vp_geometry* out);
+/* Perspective::flat2field / field2flat, src/Perspective.cpp:127-133 */
+VP_API int vp_flat2field(const vp_geometry* g, const float flat[2], float field[2]);
+VP_API int vp_field2flat(const vp_geometry* g, const float field[2], float flat[2]);
+/* the launch scalars of src/Resources.cpp:159-163 and src/main.cpp:283-289 -> vp_params for the fused entry points */
+VP_API int vp_geometry_params(const vp_geometry* g, int fmt, int wq, int hq, double max_bot_height, float circ_threshold, int max_blobs,
+                              int sample_mode, vp_params* out);
+
 typedef struct vp_ctx vp_ctx;   /* class OpenCL, opencl.h:69-112: device + in-order queue + pools */
 typedef struct vp_buf vp_buf;   /* class CLArray / RawImage storage, opencl.h:154-188 */
 typedef struct vp_img vp_img;   /* class CLImage storage, opencl.h:195-212 */

@@ -2,6 +2,7 @@
 import math
 
 import numpy as np
+import pytest
 
 from vpb200 import geometry as G, synth as S
 
@@ -64,3 +65,92 @@ def test_renderer_is_deterministic_and_places_blobs():
     assert len(gt["balls"]) == 1 and len(gt["robots_yellow"]) + len(gt["robots_blue"]) == 1
     assert len(sc.blobs()) == 6                                                        # 5 pattern blobs + 1 ball
     assert S.mosaic(np.zeros((4, 4, 3), np.uint8), S.FMT_BGR).shape == (4, 4, 3)
+
+
+# ---- the C++ host derivation behind the C ABI (vision-processor_b200/host/geometry.cpp) against the numpy restatement ----
+def _calib_of(cam: G.CameraModel):
+    """SSL_GeometryCameraCalibration of a CameraModel, as CameraModel::getProto writes it (src/CameraModel.cpp:90-112)."""
+    from vpb200 import lib
+    w, x, y, z = cam.quat_wxyz
+    t = cam.f2i() @ (-np.asarray(cam.pos, np.float32))
+    return lib.CameraCalib(cam.size[0], cam.size[1], cam.focal_length, cam.principal_point[0], cam.principal_point[1], cam.distortion_k2,
+                           x, y, z, w, float(t[0]), float(t[1]), float(t[2]))
+
+
+def _field_c(f: G.FieldSize):
+    from vpb200 import lib
+    return lib.FieldSizeC(f.field_length, f.field_width, f.boundary_width, -1.0 if f.boundary_width_goal_line is None else f.boundary_width_goal_line,
+                          f.ball_radius)
+
+
+CAMERAS = [
+    dict(cam=lambda: G.default_camera(1224, 1024), size=(1224, 1024)),
+    dict(cam=lambda: G.default_camera(612, 512, k2=0.12), size=(612, 512)),
+    dict(cam=lambda: G.CameraModel(size=(640, 480), focal_length=700.0, principal_point=(322.0, 238.0), distortion_k2=0.11, pos=(1500.0, -800.0, 4000.0),
+                                   quat_wxyz=(0.05, -0.99, 0.02, 0.1)), size=(320, 240)),  # ensureSize halves it
+]
+
+
+@pytest.mark.parametrize("case", CAMERAS)
+def test_host_geometry_matches_the_numpy_restatement(case):
+    from vpb200 import lib
+    cam = case["cam"]()
+    ref = G.Perspective(case["cam"]())
+    ref.geometry_check(*case["size"], 180.0, sequential_fp32=True)                     # the reference's own summation order
+    hp = lib.HostPerspective(_calib_of(cam), _field_c(ref.field))
+    hp.geometry_check(*case["size"], 180.0)
+    assert hp.sees_field
+    # the camera position survives the round trip through (q, t); the 72 kernel-argument bytes agree to rounding
+    want = np.frombuffer(G.pack_cl_camera_model(ref.model), np.uint8)
+    got = np.frombuffer(bytes(hp.model), np.uint8)
+    assert got[:8].tolist() == want[:8].tolist()                                       # shape
+    np.testing.assert_allclose(got[8:].view("<f4"), want[8:].view("<f4"), rtol=2e-6, atol=2e-3)
+    # both accumulate the field scale sequentially in fp32 (Perspective.cpp:78-91); the terms differ by an ulp here and there
+    assert abs(hp.field_scale - ref.field_scale) < 2e-5 * ref.field_scale
+    np.testing.assert_allclose(hp.visible_field_extent, ref.visible_field_extent, rtol=1e-6, atol=2e-2)
+    assert hp.reprojected_field_size == ref.reprojected_field_size
+    assert (hp.min_blob_radius, hp.max_blob_radius) == (ref.min_blob_radius, ref.max_blob_radius)
+    lp = G.launch_params(ref, 0, *case["size"])
+    p = hp.params(0, *case["size"])
+    assert (p.wf, p.hf, p.grad_offset, p.circle_radius, p.blob_radius, p.max_blobs) == (lp.wf, lp.hf, lp.grad_offset, lp.circle_radius, lp.blob_radius,
+                                                                                      lp.max_blobs)
+    assert p.min_score == 0.0 and p.circ_threshold == 15.0 and p.wf % 2 == 0 and p.hf % 2 == 0
+    # point transforms
+    px = np.array([[10.0, 20.0], [case["size"][0] / 2, case["size"][1] / 2], [case["size"][0] - 3.0, case["size"][1] - 7.0]], np.float32)
+    fld = hp.image2field(px, 150.0)
+    np.testing.assert_allclose(fld, ref.model.image2field(px, 150.0), rtol=1e-5, atol=5e-2)
+    np.testing.assert_allclose(hp.field2image(fld), px, atol=3e-2)                     # 10 iterations invert the distortion
+    np.testing.assert_allclose(hp.field2flat(hp.flat2field(px)), px, atol=1e-3)
+    np.testing.assert_allclose(hp.flat2field(px), ref.flat2field(px), rtol=1e-5, atol=5e-2)
+
+
+def test_host_geometry_of_a_camera_that_does_not_see_the_field():
+    from vpb200 import lib
+    cam = G.default_camera(64, 48)
+    cam.pos = (50000.0, 0.0, 5000.0)                                                   # far outside the field
+    hp = lib.HostPerspective(_calib_of(cam), _field_c(G.FieldSize()))
+    hp.geometry_check(64, 48, 180.0)
+    assert not hp.sees_field and math.isnan(hp.field_scale)                            # 0/0 like the reference
+    with pytest.raises(lib.VpError):
+        hp.params(0, 64, 48)
+
+
+def test_host_geometry_rejects_bad_arguments():
+    from vpb200 import lib
+    bad = lib.CameraCalib(0, 0, -1.0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0)
+    with pytest.raises(lib.VpError):
+        lib.HostPerspective(bad, _field_c(G.FieldSize()))
+
+
+def test_reference_summation_order_inflates_the_field_scale_at_full_size():
+    """Perspective.cpp:78-91 adds 2.5 M distances of ~3.94 mm into one fp32: past 2^23 every `dx + dy` of 7.88 is absorbed
+    as 8.  The C++ derivation follows the reference; the benchmark configuration uses the true mean."""
+    from vpb200 import lib
+    cam = G.default_camera(1224, 1024)
+    true_mean = G.Perspective(G.default_camera(1224, 1024))
+    true_mean.geometry_check(1224, 1024, 180.0)
+    hp = lib.HostPerspective(_calib_of(cam), _field_c(G.FieldSize()))
+    hp.geometry_check(1224, 1024, 180.0)
+    assert abs(true_mean.field_scale - 4820 / 1224) < 1e-3 and true_mean.reprojected_field_size == (1224, 1024)
+    assert 1.010 < hp.field_scale / true_mean.field_scale < 1.015
+    assert hp.reprojected_field_size == (1208, 1010)                                   # instead of 1224 x 1024

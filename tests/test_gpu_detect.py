@@ -269,3 +269,33 @@ def test_full_size_headline_config(ctx, port):
     common.assert_float_images_equal(got["circ"], want["circ"])
     check_frame(got, 0, want)
     assert len(want["matches"]) >= 16 * 5  # every pattern blob is a peak
+
+
+def test_full_size_with_host_derived_parameters(ctx, port):
+    """Calibration -> vp_camera_model_from_calib -> vp_geometry_check -> vp_geometry_params -> fused detection: the launch
+    scalars come from the C++ host derivation (reference summation order: 3.987 mm/px, flat 1208 x 1010), the frame is the
+    headline 2448x2048 scene; bit-exact against the oracle run with the same scalars."""
+    from vpb200 import geometry as G, synth as S
+    wq, hq = 1224, 1024
+    cam = G.default_camera(wq, hq, k2=0.03)
+    w, x, y, z = cam.quat_wxyz
+    t = cam.f2i() @ (-np.asarray(cam.pos, np.float32))
+    calib = lib.CameraCalib(wq, hq, cam.focal_length, cam.principal_point[0], cam.principal_point[1], cam.distortion_k2, x, y, z, w,
+                            float(t[0]), float(t[1]), float(t[2]))
+    f = G.FieldSize()
+    hp = lib.HostPerspective(calib, lib.FieldSizeC(f.field_length, f.field_width, f.boundary_width, f.boundary_width_goal_line, f.ball_radius))
+    hp.geometry_check(wq, hq, 180.0)
+    vp = hp.params(0, wq, hq)
+    assert vp.wf % 2 == 0 and vp.hf % 2 == 0 and (vp.wf, vp.hf) != (wq, hq)
+    scene = S.random_scene(hp.visible_field_extent, 16, 4, seed=2)
+    raw = S.render_raw(scene, cam, 2 * wq, 2 * hq, seed=2).reshape(-1)
+    po = O.Params()
+    assert C.sizeof(po) == C.sizeof(vp)
+    C.memmove(C.byref(po), C.byref(vp), C.sizeof(vp))
+    want = port.detect(raw, po)
+    got = ctx.detect(raw, vp)
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+    assert want["counter"][0] >= 60

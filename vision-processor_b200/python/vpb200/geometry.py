@@ -130,8 +130,16 @@ class Perspective:
     min_blob_radius: float = 20.0
     max_blob_radius: float = 25.0
 
-    def geometry_check(self, width: int, height: int, max_bot_height: float, resampling_factor: float = 1.0) -> None:
-        """src/Perspective.cpp:35-125 (width/height in quad px for Bayer cameras)."""
+    def geometry_check(self, width: int, height: int, max_bot_height: float, resampling_factor: float = 1.0,
+                       sequential_fp32: bool = False) -> None:
+        """src/Perspective.cpp:35-125 (width/height in quad px for Bayer cameras).
+
+        ``sequential_fp32``: the reference accumulates the neighbour distances in ONE fp32 variable in raster order
+        (``fieldScaleSum += dx + dy``, Perspective.cpp:78-91).  At 1224x1024 that sum passes 2^23 after ~1 M pixels, every
+        further 7.88 is absorbed as 8, and the resulting scale is 1.2 % larger than the true mean (3.987 vs 3.938 mm/px).
+        The default here is the true mean (float64 sum) -- the configuration SURVEY 8(d) fixes for the benchmark (flat size
+        == quad size); ``sequential_fp32=True`` reproduces the reference's arithmetic, which is what the C++ derivation
+        behind the C ABI (host/geometry.cpp) does."""
         m, f = self.model, self.field
         m.ensure_size((width, height))
         self.min_blob_radius = min(CENTER_BLOB_RADIUS, SIDE_BLOB_RADIUS, f.ball_radius)  # :69
@@ -146,8 +154,13 @@ class Perspective:
         dx = np.linalg.norm(pts[:-1, 1:] - pos, axis=-1)
         dy = np.linalg.norm(pts[1:, :-1] - pos, axis=-1)
         n = 2 * int(inside.sum())
-        s = float((dx[inside].astype(np.float64) + dy[inside].astype(np.float64)).sum())
-        self.field_scale = float(F32(F32(s / n) * F32(resampling_factor)))
+        if sequential_fp32:
+            terms = (dx[inside] + dy[inside]).astype(F32)  # boolean indexing keeps raster order
+            s = float(np.cumsum(terms, dtype=F32)[-1]) if len(terms) else 0.0  # cumsum adds sequentially, np.sum pairwise
+            self.field_scale = float(F32(F32(s) / F32(n)) * F32(resampling_factor)) if n else float("nan")
+        else:
+            s = float((dx[inside].astype(np.float64) + dy[inside].astype(np.float64)).sum())
+            self.field_scale = float(F32(F32(s / n) * F32(resampling_factor)))
 
         # :94-105 visible extent from the image border
         border = np.concatenate([

@@ -66,6 +66,27 @@ class Params(C.Structure):
 assert C.sizeof(CameraModel) == 72
 
 
+class CameraCalib(C.Structure):
+    """vp_camera_calib: the SSL_GeometryCameraCalibration fields CameraModel reads (src/CameraModel.cpp:80-88)."""
+    _fields_ = [("pixel_image_width", C.c_int32), ("pixel_image_height", C.c_int32), ("focal_length", C.c_float),
+                ("principal_point_x", C.c_float), ("principal_point_y", C.c_float), ("distortion", C.c_float),
+                ("q0", C.c_float), ("q1", C.c_float), ("q2", C.c_float), ("q3", C.c_float),
+                ("tx", C.c_float), ("ty", C.c_float), ("tz", C.c_float)]
+
+
+class FieldSizeC(C.Structure):
+    """vp_field_size."""
+    _fields_ = [("field_length", C.c_float), ("field_width", C.c_float), ("boundary_width", C.c_float),
+                ("boundary_width_goal_line", C.c_float), ("ball_radius", C.c_float)]
+
+
+class Geometry(C.Structure):
+    """vp_geometry: what Perspective::geometryCheck leaves behind (src/Perspective.h:32-58)."""
+    _fields_ = [("model", CameraModel), ("field_scale", C.c_float), ("visible_field_extent", C.c_float * 4),
+                ("reprojected_field_size", C.c_int32 * 2), ("min_blob_radius", C.c_float), ("max_blob_radius", C.c_float),
+                ("min_field_scale", C.c_float), ("max_field_scale", C.c_float)]
+
+
 def camera_model_from_bytes(b: bytes) -> CameraModel:
     assert len(b) == 72
     m = CameraModel()
@@ -108,6 +129,15 @@ def load() -> C.CDLL:
     sigs = {
         "vp_version": (C.c_char_p, []),
         "vp_format_pixel_size": (C.c_int, [C.c_int]),
+        "vp_camera_model_from_calib": (C.c_int, [C.POINTER(CameraCalib), C.POINTER(CameraModel)]),
+        "vp_camera_model_ensure_size": (C.c_int, [C.POINTER(CameraModel), C.c_int, C.c_int]),
+        "vp_field2image": (C.c_int, [C.POINTER(CameraModel), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "vp_image2field": (C.c_int, [C.POINTER(CameraModel), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]),
+        "vp_geometry_check": (C.c_int, [C.POINTER(CameraModel), C.POINTER(FieldSizeC), C.c_int, C.c_int, C.c_double, C.c_float, C.c_float,
+                                        C.POINTER(Geometry)]),
+        "vp_flat2field": (C.c_int, [C.POINTER(Geometry), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "vp_field2flat": (C.c_int, [C.POINTER(Geometry), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+        "vp_geometry_params": (C.c_int, [C.POINTER(Geometry), C.c_int, C.c_int, C.c_int, C.c_double, C.c_float, C.c_int, C.c_int, C.POINTER(Params)]),
         "vp_device_count": (C.c_int, []),
         "vp_last_error": (C.c_char_p, [vp]),
         "vp_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
@@ -182,6 +212,67 @@ def bound_symbols() -> list:
 
 def device_count() -> int:
     return int(load().vp_device_count())
+
+
+def _ck_host(rc: int, what: str, allow=()) -> int:
+    if rc != 0 and rc not in allow:
+        raise VpError(rc, what)
+    return rc
+
+
+class HostPerspective:
+    """The host-side derivation behind the C ABI (vision-processor_b200/host/geometry.cpp), with the member names of the
+    reference's ``Perspective`` (src/Perspective.h:32-58): model, fieldScale, visibleFieldExtent, reprojectedFieldSize,
+    minBlobRadius, maxBlobRadius; geometryCheck, flat2field, field2flat.  CPU only, no context needed."""
+
+    def __init__(self, calib: CameraCalib, field: FieldSizeC, geometry_tolerance: float = 10.0):
+        self.lib = load()
+        self.model = CameraModel()
+        _ck_host(self.lib.vp_camera_model_from_calib(C.byref(calib), C.byref(self.model)), "vp_camera_model_from_calib")
+        self.field = field
+        self.geometry_tolerance = geometry_tolerance
+        self.geometry = Geometry()
+        self.sees_field = False
+
+    def geometry_check(self, width: int, height: int, max_bot_height: float, resampling_factor: float = 1.0) -> None:
+        rc = _ck_host(self.lib.vp_geometry_check(C.byref(self.model), C.byref(self.field), width, height, max_bot_height, resampling_factor,
+                                                 self.geometry_tolerance, C.byref(self.geometry)), "vp_geometry_check", allow=(4,))
+        self.sees_field = rc == 0
+        self.model = self.geometry.model
+
+    field_scale = property(lambda self: float(self.geometry.field_scale))
+    visible_field_extent = property(lambda self: tuple(self.geometry.visible_field_extent))
+    reprojected_field_size = property(lambda self: tuple(self.geometry.reprojected_field_size))
+    min_blob_radius = property(lambda self: float(self.geometry.min_blob_radius))
+    max_blob_radius = property(lambda self: float(self.geometry.max_blob_radius))
+
+    def _xy(self, fn, a, n_in: int, n_out: int, *extra) -> np.ndarray:
+        a = np.asarray(a, np.float32).reshape(-1, n_in)
+        out = np.empty((len(a), n_out), np.float32)
+        for i in range(len(a)):
+            src, dst = (C.c_float * n_in)(*a[i]), (C.c_float * n_out)()
+            _ck_host(fn(*extra[:1], src, *extra[1:], dst), fn.__name__)
+            out[i] = list(dst)
+        return out
+
+    def flat2field(self, pos) -> np.ndarray:
+        return self._xy(self.lib.vp_flat2field, pos, 2, 2, C.byref(self.geometry))
+
+    def field2flat(self, pos) -> np.ndarray:
+        return self._xy(self.lib.vp_field2flat, pos, 2, 2, C.byref(self.geometry))
+
+    def field2image(self, pos) -> np.ndarray:
+        return self._xy(self.lib.vp_field2image, pos, 3, 2, C.byref(self.model))
+
+    def image2field(self, pos, height: float) -> np.ndarray:
+        return self._xy(self.lib.vp_image2field, pos, 2, 3, C.byref(self.model), C.c_float(height))
+
+    def params(self, fmt: int, wq: int, hq: int, max_bot_height: float = 180.0, circ_threshold: float = 15.0, max_blobs: int = 2000,
+               sample_mode: int = 0) -> Params:
+        p = Params()
+        _ck_host(self.lib.vp_geometry_params(C.byref(self.geometry), fmt, wq, hq, max_bot_height, circ_threshold, max_blobs, sample_mode, C.byref(p)),
+                 "vp_geometry_params")
+        return p
 
 
 def _np_ptr(a: np.ndarray) -> C.c_void_p:
