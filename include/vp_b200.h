@@ -246,6 +246,13 @@ VP_API int vp_raw2nv12_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq
 VP_API int vp_raw2rgba_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_rgba, int sample_mode);
 VP_API int vp_rgba2nv12_device(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_t* d_nv12);
 VP_API int vp_f2nv12_device(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_nv12);
+/* the same conversions for n dense frames in ONE launch (the four debug views of main.cpp:380-393 over a batch); NV12 frame
+ * i is written at d_nv12 + i*nv12_stride, nv12_stride >= 1.5*w*h (the reference allocates 2*w*h, opencl.cpp:27).  The
+ * result stays in device memory, where a hardware encoder session can take it (rtpstreamer.cpp:62: h264_nvenc first). */
+VP_API int vp_rgba2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_rgba, int n_frames, int w, int h, uint8_t* d_nv12, size_t nv12_stride);
+VP_API int vp_f2nv12_batch_device(vp_ctx* ctx, const float* d_f32, int n_frames, int w, int h, uint8_t* d_nv12, size_t nv12_stride);
+VP_API int vp_raw2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, int fmt, int wq, int hq, uint8_t* d_nv12, size_t nv12_stride,
+                                    int sample_mode);
 
 /* blocking copies ordered after everything enqueued on the context stream (tests, tools) */
 VP_API int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes);

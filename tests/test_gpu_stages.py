@@ -183,3 +183,32 @@ def test_errors_are_reported_not_fatal(ctx):
         ctx.gradient_dot(np.zeros((4, 4), np.uint8), 1)  # U8 image where RGBA8 is required
     assert e.value.code == 1
     assert "RGBA8" in str(e.value)
+
+
+def test_batched_nv12_views_match_the_per_frame_calls(ctx, port):
+    """The three debug-stream conversions over a batch in one launch (main.cpp:380-393's views for n frames), with a frame
+    stride larger than the 1.5*w*h that is written."""
+    rng = np.random.default_rng(5)
+    n, w, h = 5, 46, 30
+    rgba = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+    f32 = (rng.standard_normal((n, h, w)) * 120).astype(np.float32)
+    used = w * h * 3 // 2
+    got = ctx.nv12_batch("rgba", rgba, w, h, stride=used + 64)
+    for i in range(n):
+        np.testing.assert_array_equal(got[i, :used], port.rgba2nv12(rgba[i])[:used])
+        assert not got[i, used:].any()                                   # nothing is written past 1.5*w*h
+    got = ctx.nv12_batch("f32", f32, w, h)
+    for i in range(n):
+        np.testing.assert_array_equal(got[i, :used], port.f2nv12(f32[i])[:used])
+    for kw in (dict(wq=48, hq=32, fmt=0), dict(wq=46, hq=30, fmt=1, k2=0.1), dict(wq=40, hq=24, fmt=2)):
+        frames = []
+        for s_ in range(3):
+            p, raw, _ = common.make_case(seed=40 + s_, **kw)
+            frames.append(raw)
+        used = p.wq * p.hq * 3 // 2
+        got = ctx.nv12_batch("raw", np.stack(frames), p.wq, p.hq, fmt=p.fmt)
+        for i, raw in enumerate(frames):
+            ch = port.raw2quad(raw, p.fmt, p.wq, p.hq)
+            np.testing.assert_array_equal(got[i, :used], port.quad2nv12(ch, p.fmt, 0)[:used])
+    with pytest.raises(lib.VpError):
+        ctx.nv12_batch("rgba", rgba, w, h, stride=used - 2)              # stride smaller than a frame

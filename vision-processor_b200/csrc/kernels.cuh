@@ -2149,11 +2149,15 @@ __device__ __forceinline__ uint32_t nv12_uv(uint32_t r, uint32_t g, uint32_t b)
 	return (uint32_t)u | ((uint32_t)v << 8);
 }
 
-__global__ void __launch_bounds__(256) k_rgba2nv12(const uint32_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h)
+/* frame = blockIdx.z: frames `in_stride` pixels / `out_stride` bytes apart (a batch of debug-stream views in one launch) */
+__global__ void __launch_bounds__(256) k_rgba2nv12(const uint32_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h, size_t in_stride = 0,
+                                                   size_t out_stride = 0)
 {
 	const int bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
 	if (2 * bx >= w)
 		return;
+	in += blockIdx.z * in_stride;
+	out += blockIdx.z * out_stride;
 	const uint2 a = __ldg(reinterpret_cast<const uint2*>(in + (size_t)(2 * by) * w + 2 * bx));
 	const uint2 b = __ldg(reinterpret_cast<const uint2*>(in + (size_t)(2 * by + 1) * w + 2 * bx));
 #define VP_Y(p) nv12_y((p) & 255u, ((p) >> 8) & 255u, ((p) >> 16) & 255u)
@@ -2169,11 +2173,14 @@ __device__ __forceinline__ uint32_t f2y(float v)
 	/* f2nv12.cl:24: convert_uchar_sat(v + 127.0f): round toward zero, saturate, NaN -> 0 */
 	return min(__float2uint_rz(__fadd_rn(v, 127.0f)), 255u);
 }
-__global__ void __launch_bounds__(256) k_f2nv12(const float* __restrict__ in, uint8_t* __restrict__ out, int w, int h)
+__global__ void __launch_bounds__(256) k_f2nv12(const float* __restrict__ in, uint8_t* __restrict__ out, int w, int h, size_t in_stride = 0,
+                                                size_t out_stride = 0)
 {
 	const int bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
 	if (2 * bx >= w)
 		return;
+	in += blockIdx.z * in_stride;
+	out += blockIdx.z * out_stride;
 	const float2 a = __ldg(reinterpret_cast<const float2*>(in + (size_t)(2 * by) * w + 2 * bx));
 	const float2 b = __ldg(reinterpret_cast<const float2*>(in + (size_t)(2 * by + 1) * w + 2 * bx));
 	*reinterpret_cast<uint16_t*>(out + (size_t)(2 * by) * w + 2 * bx) = (uint16_t)(f2y(a.x) | (f2y(a.y) << 8));
@@ -2182,11 +2189,13 @@ __global__ void __launch_bounds__(256) k_f2nv12(const float* __restrict__ in, ui
 }
 
 template <int FMT, int MODE, class Src>
-__global__ void __launch_bounds__(256) k_quad2nv12(Src s, uint8_t* __restrict__ out, int wq, int hq)
+__global__ void __launch_bounds__(256) k_quad2nv12(Src s0, uint8_t* __restrict__ out, int wq, int hq, size_t src_stride = 0, size_t out_stride = 0)
 {
 	const int bx = blockIdx.x * 256 + threadIdx.x, by = blockIdx.y;
 	if (2 * bx >= wq)
 		return;
+	const Src s = src_frame(s0, blockIdx.z * src_stride);
+	out += blockIdx.z * out_stride;
 	uint32_t yv[4], r, g, b;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {

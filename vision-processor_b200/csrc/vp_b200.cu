@@ -275,10 +275,10 @@ int launch_reproject(vp_ctx* ctx, cudaStream_t stream, const Src& src, size_t fr
 }
 
 template <class Src>
-int launch_quad2nv12(vp_ctx* ctx, const Src& src, int fmt, int mode, uint8_t* out, int wq, int hq)
+int launch_quad2nv12(vp_ctx* ctx, const Src& src, int fmt, int mode, uint8_t* out, int wq, int hq, int n = 1, size_t src_stride = 0, size_t out_stride = 0)
 {
-	const dim3 g(cdiv(wq / 2, 256), hq / 2);
-#define VP_CALL k_quad2nv12<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, out, wq, hq)
+	const dim3 g(cdiv(wq / 2, 256), hq / 2, n);
+#define VP_CALL k_quad2nv12<FMTC, MODE, Src><<<g, 256, 0, ctx->stream>>>(src, out, wq, hq, src_stride, out_stride)
 	if (fmt == VP_FMT_RGGB8) { VP_DISPATCH_MODE(FMT_RGGB, mode, VP_CALL) }
 	else if (fmt == VP_FMT_GRBG8) { VP_DISPATCH_MODE(FMT_GRBG, mode, VP_CALL) }
 	else { VP_DISPATCH_MODE(FMT_BGR, mode, VP_CALL) }
@@ -1075,14 +1075,59 @@ int vp_quad2rgba(vp_ctx* ctx, vp_img* const ch[4], int fmt, vp_img* rgba, int mo
 	return launch_quad2rgba(ctx, planes_of(ch, fmt), fmt, mode, (uint32_t*)rgba->buf->d, wq, hq);
 }
 
-static int raw_src_launch_nv12(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* out, int mode)
+static int raw_src_launch_nv12(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* out, int mode, int n = 1, size_t out_stride = 0)
 {
+	const size_t src_stride = (size_t)wq * hq * (size_t)vp_format_pixel_size(fmt); /* frames of a batch are dense */
 	if (fmt == VP_FMT_BGR8) {
 		SrcBGR s{ d_raw, wq };
-		return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq);
+		return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq, n, src_stride, out_stride);
 	}
 	SrcBayer s{ d_raw, 2 * wq };
-	return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq);
+	return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq, n, src_stride, out_stride);
+}
+
+/* ---- batched debug-stream conversions: n frames, one launch (the NV12 view stays in device memory, where
+ * an NVENC session -- rtpstreamer.cpp:62 prefers h264_nvenc -- can take it without the 1.9 MB read-map per frame) ---- */
+static int check_nv12_batch(vp_ctx* ctx, const void* in, const void* out, int n, int w, int h, size_t stride)
+{
+	REQUIRE(ctx, ctx && in && out, "null argument");
+	REQUIRE(ctx, n >= 0 && w >= 0 && h >= 0 && (w % 2) == 0 && (h % 2) == 0, "NV12 needs even dimensions, got %dx%d (n = %d)", w, h, n);
+	REQUIRE(ctx, n <= 65535, "at most 65535 frames per call");
+	REQUIRE(ctx, stride >= (size_t)w * h * 3 / 2, "NV12 frame stride %zu smaller than 1.5*w*h", stride);
+	return VP_OK;
+}
+
+int vp_rgba2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_rgba, int n_frames, int w, int h, uint8_t* d_nv12, size_t nv12_stride)
+{
+	int rc = check_nv12_batch(ctx, d_rgba, d_nv12, n_frames, w, h, nv12_stride);
+	if (rc) return rc;
+	if (n_frames == 0 || w == 0 || h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "rgba2nv12");
+	k_rgba2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n_frames), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h, (size_t)w * h, nv12_stride);
+	return check_launch(ctx, "k_rgba2nv12");
+}
+
+int vp_f2nv12_batch_device(vp_ctx* ctx, const float* d_f32, int n_frames, int w, int h, uint8_t* d_nv12, size_t nv12_stride)
+{
+	int rc = check_nv12_batch(ctx, d_f32, d_nv12, n_frames, w, h, nv12_stride);
+	if (rc) return rc;
+	if (n_frames == 0 || w == 0 || h == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "f2nv12");
+	k_f2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n_frames), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h, (size_t)w * h, nv12_stride);
+	return check_launch(ctx, "k_f2nv12");
+}
+
+int vp_raw2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, int fmt, int wq, int hq, uint8_t* d_nv12, size_t nv12_stride, int mode)
+{
+	REQUIRE(ctx, ctx && is_raw_fmt(fmt) && is_mode(mode), "bad format or sample mode");
+	int rc = check_nv12_batch(ctx, d_raw, d_nv12, n_frames, wq, hq, nv12_stride);
+	if (rc) return rc;
+	if (n_frames == 0 || wq == 0 || hq == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "raw2nv12");
+	return raw_src_launch_nv12(ctx, d_raw, fmt, wq, hq, d_nv12, mode, n_frames, nv12_stride);
 }
 
 int vp_raw2nv12_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_nv12, int mode)

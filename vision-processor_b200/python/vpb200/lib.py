@@ -192,6 +192,9 @@ def load() -> C.CDLL:
         "vp_raw2rgba_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]),
         "vp_rgba2nv12_device": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
         "vp_f2nv12_device": (C.c_int, [vp, vp, C.c_int, C.c_int, vp]),
+        "vp_rgba2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
+        "vp_f2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
+        "vp_raw2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int]),
         "vp_copy_to_host": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_copy_to_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
@@ -652,6 +655,26 @@ class Context:
         src.release()
         dst.release()
         return out
+
+    def nv12_batch(self, kind: str, frames: np.ndarray, w: int, h: int, fmt: int = 0, mode: int = 0, stride: int | None = None) -> np.ndarray:
+        """n frames -> n NV12 views in one launch.  kind: 'rgba' (n,h,w,4 u8), 'f32' (n,h,w f32) or 'raw' (n raw frames)."""
+        frames = np.ascontiguousarray(frames)
+        n = len(frames)
+        stride = 2 * w * h if stride is None else stride
+        src = self.buffer(max(frames.nbytes, 1), frames.reshape(-1).view(np.uint8))
+        dst = self.buffer(max(n * stride, 1), np.zeros(max(n * stride, 1), np.uint8))
+        if kind == "rgba":
+            rc = self.lib.vp_rgba2nv12_batch_device(self.h, C.c_void_p(src.device_ptr), n, w, h, C.c_void_p(dst.device_ptr), stride)
+        elif kind == "f32":
+            rc = self.lib.vp_f2nv12_batch_device(self.h, C.c_void_p(src.device_ptr), n, w, h, C.c_void_p(dst.device_ptr), stride)
+        else:
+            rc = self.lib.vp_raw2nv12_batch_device(self.h, C.c_void_p(src.device_ptr), n, fmt, w, h, C.c_void_p(dst.device_ptr), stride, mode)
+        try:
+            self._ck(rc)
+            return dst.read()[:n * stride].reshape(n, stride)
+        finally:
+            src.release()
+            dst.release()
 
     def raw2rgba(self, raw: np.ndarray, fmt, wq, hq, mode=0):
         src = self.buffer(raw.nbytes, raw)
