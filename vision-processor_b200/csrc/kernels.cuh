@@ -611,13 +611,14 @@ __device__ __forceinline__ float2 add2_opaque(float2 a, float2 b, unsigned long 
 	return bits_f2(r);
 }
 
-/* the per-frame arithmetic of one thread's four pixels (rows ly, ly+4, ly+8, ly+12 of the tile) */
-template <int FMT, bool FULL>
-__device__ __forceinline__ void hoist_blend(const float* __restrict__ T, const float2 (&W)[4][8], const int (&O)[4][4], uint32_t* __restrict__ out, int wf,
+/* the per-frame arithmetic of one thread's PX pixels (rows ly, ly+RS, ly+2RS, ... of the tile, RS = 16/PX) */
+template <int FMT, bool FULL, int PX>
+__device__ __forceinline__ void hoist_blend(const float* __restrict__ T, const float2 (&W)[PX][8], const int (&O)[PX][4], uint32_t* __restrict__ out, int wf,
                                             bool okx, int rows_ok, unsigned long long one2)
 {
+	constexpr int RS = FT_H / PX;
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
+	for (int k = 0; k < PX; k++) {
 		const float* t0 = T + O[k][0];
 		const float* t1 = T + O[k][1];
 		const float* t2 = T + O[k][2];
@@ -637,8 +638,8 @@ __device__ __forceinline__ void hoist_blend(const float* __restrict__ T, const f
 		const float2 rb = add2(vb, make_float2(8388608.0f, 8388608.0f));
 		const uint32_t v0 = __float_as_uint(ra.x), v1 = __float_as_uint(ra.y), v2 = __float_as_uint(rb.x), v3 = __float_as_uint(rb.y);
 		const uint32_t px = FMT == FMT_RGGB ? drgb_biased(v0, (v1 >> 1) + (v2 >> 1), v3) : drgb_biased(v1, (v0 >> 1) + (v3 >> 1), v2);
-		if (FULL || (okx && 4 * k < rows_ok))
-			out[(uint32_t)(4 * k) * (uint32_t)wf] = px;
+		if (FULL || (okx && RS * k < rows_ok))
+			out[(uint32_t)(RS * k) * (uint32_t)wf] = px;
 	}
 }
 
@@ -676,8 +677,9 @@ template <int V> struct IntC { static constexpr int value = V; };
  * finished blending goes straight on to converting.
  * Staging plan: lanes 2k and 2k+1 take vector k of two staged rows ONE pitch apart; the pitch is 21 chunks of 16 bytes,
  * so the eight lanes of a store phase hit eight different bank groups (a pitch of 20 gave 2-way conflicts). */
-template <int FMT>
-__global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+/* PX = pixels per thread: 4 (256 threads, 128 registers, 2 CTAs/SM) or 2 (512 threads, 64 registers, 2 CTAs/SM = twice the warps) */
+template <int FMT, int PX>
+__global__ void __launch_bounds__(1024 / PX, 2) k_reproject_hoist(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
                                                               const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq,
                                                               int wf, int hf, int n_frames, int chunk, float one)
 {
@@ -688,15 +690,17 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 	const int f0 = blockIdx.z * chunk;
 	const int n = min(n_frames, f0 + chunk) - f0;
 	const TileEntry e = table[ty * gridDim.x + tx];
+	constexpr int NT = 1024 / PX, RS = FT_H / PX; /* threads per CTA; row distance between a thread's pixels */
+	constexpr int NSLOT = (HNV * 2 * TQ_H + NT - 1) / NT; /* raw vectors per thread */
 	const int tid = threadIdx.x;
 	const int lx = tid & 63, ly = tid >> 6;
 	const int gx = tx * FT_W + lx;
 	const uint32_t nfl = (uint32_t)wf * (uint32_t)hf;
 	const uint8_t* const raw = raw0 + (size_t)f0 * frame_stride;
-	float2 pos[4]; /* requested first: nothing below depends on them until the weights are derived */
+	float2 pos[PX]; /* requested first: nothing below depends on them until the weights are derived */
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const int gy = ty * FT_H + ly + 4 * k;
+	for (int k = 0; k < PX; k++) {
+		const int gy = ty * FT_H + ly + RS * k;
 		pos[k] = make_float2(0.f, 0.f);
 		if (gx < wf && gy < hf)
 			pos[k] = __ldg(lut + (gy * wf + gx));
@@ -708,8 +712,8 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 			const uint8_t* rawf = raw + (size_t)f * frame_stride;
 			uint32_t* out = flat + (size_t)(f0 + f) * nfl;
 #pragma unroll 1
-			for (int k = 0; k < 4; k++) {
-				const int gy = ty * FT_H + ly + 4 * k;
+			for (int k = 0; k < PX; k++) {
+				const int gy = ty * FT_H + ly + RS * k;
 				if (gx < wf && gy < hf) {
 					const float2 pos = __ldg(lut + (gy * wf + gx));
 					uint32_t v;
@@ -732,11 +736,11 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 	const int row_bytes = 2 * wq;
 	const bool vec = (e.flags & 2) != 0;
 	const int n_rr = 2 * e.height; /* raw rows to stage: rr = 2*j + s -> staged row j of planes (2s, 2s+1) */
-	const uint8_t* s_src[2]; /* this thread's vector i in the next frame to copy */
-	int s_dst[2], s_edge[2]; /* s_edge < 0: no vector */
+	const uint8_t* s_src[NSLOT]; /* this thread's vector i in the next frame to copy */
+	int s_dst[NSLOT], s_edge[NSLOT]; /* s_edge < 0: no vector */
 #pragma unroll
-	for (int i = 0; i < 2; i++) {
-		const int v = tid + 256 * i;
+	for (int i = 0; i < NSLOT; i++) {
+		const int v = tid + NT * i;
 		const int q4 = v / (4 * HNV), w = v - q4 * (4 * HNV);
 		const int half = w >= 2 * HNV ? 1 : 0, w2 = w - half * 2 * HNV;
 		const int cv = w2 >> 1, rr = 4 * q4 + half + 2 * (w2 & 1);
@@ -752,14 +756,14 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 			s_edge[i] = qx0 < 0 ? 1 : (qx0 != qxc ? 2 : 0);
 		}
 	}
-	unsigned char* const my_ring = ring + tid * 16; /* vector i of stage st: my_ring + st*HRING + i*4096 */
+	unsigned char* const my_ring = ring + tid * 16; /* vector i of stage st: my_ring + st*HRING + i*NT*16 */
 	int to_copy = n;                                /* frames not yet requested */
 	auto issue_copy = [&](auto STAGE) {             /* next frame into R[STAGE]; always commits, possibly an empty group */
 		if (to_copy > 0) {
 #pragma unroll
-			for (int i = 0; i < 2; i++) {
+			for (int i = 0; i < NSLOT; i++) {
 				if (s_edge[i] >= 0)
-					cp_async16(my_ring + decltype(STAGE)::value * HRING + i * 4096, s_src[i]);
+					cp_async16(my_ring + decltype(STAGE)::value * HRING + i * NT * 16, s_src[i]);
 				s_src[i] += frame_stride;
 			}
 		}
@@ -772,12 +776,12 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 		float* Tb = T + PAR * HT;
 		if (vec) {
 #pragma unroll
-			for (int i = 0; i < 2; i++)
+			for (int i = 0; i < NSLOT; i++)
 				if (s_edge[i] >= 0)
-					hoist_convert(*reinterpret_cast<const uint4*>(my_ring + PAR * HRING + i * 4096), s_edge[i], Tb + s_dst[i]);
+					hoist_convert(*reinterpret_cast<const uint4*>(my_ring + PAR * HRING + i * NT * 16), s_edge[i], Tb + s_dst[i]);
 		} else { /* raw rows not 16-byte aligned (wq % 8 != 0): per-texel gather with the edge replicated */
 			const int tot = 4 * e.height * TQ_W;
-			for (int v = tid; v < tot; v += 256) {
+			for (int v = tid; v < tot; v += NT) {
 				const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
 				const int jj = rc >> 2, c = rc & 3;
 				const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
@@ -790,12 +794,12 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 	issue_copy(IntC<1>{});
 
 	/* ---- frame-invariant part: weights and tap offsets of this thread's four pixels (the copies are in flight) ---- */
-	float2 W[4][8];
-	int O[4][4];
+	float2 W[PX][8];
+	int O[PX][4];
 	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
 #pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const int gy = ty * FT_H + ly + 4 * k;
+	for (int k = 0; k < PX; k++) {
+		const int gy = ty * FT_H + ly + RS * k;
 		const bool ok = gx < wf && gy < hf;
 		int ixp, ixn, iyp, iyn;
 		float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
@@ -812,9 +816,9 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 		O[k][3] = ok ? 3 * HPLANE + iyn * HP + ixn : 0;
 	}
 	const bool okx = gx < wf;
-	const int rows_ok = hf - (ty * FT_H + ly);                        /* pixel k is inside the image iff 4k < rows_ok */
+	const int rows_ok = hf - (ty * FT_H + ly);                        /* pixel k is inside the image iff RS*k < rows_ok */
 	const bool full = (tx + 1) * FT_W <= wf && (ty + 1) * FT_H <= hf; /* CTA-uniform: no per-pixel predicates */
-	uint32_t* out = flat + (size_t)f0 * nfl + ((uint32_t)(ty * FT_H + ly) * (uint32_t)wf + (uint32_t)gx); /* pixel k adds 4*k*wf */
+	uint32_t* out = flat + (size_t)f0 * nfl + ((uint32_t)(ty * FT_H + ly) * (uint32_t)wf + (uint32_t)gx); /* pixel k adds RS*k*wf */
 	const unsigned long long one2 = f2_bits(make_float2(one, one));
 
 	cp_async_wait<1>();
@@ -825,9 +829,9 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist(const uint8_t* __res
 		constexpr int PAR = decltype(PARC)::value;
 		issue_copy(PARC);
 		if (full)
-			hoist_blend<FMT, true>(T + PAR * HT, W, O, out, wf, true, 16, one2);
+			hoist_blend<FMT, true, PX>(T + PAR * HT, W, O, out, wf, true, 16, one2);
 		else
-			hoist_blend<FMT, false>(T + PAR * HT, W, O, out, wf, okx, rows_ok, one2);
+			hoist_blend<FMT, false, PX>(T + PAR * HT, W, O, out, wf, okx, rows_ok, one2);
 		out += nfl;
 		left--;
 		cp_async_wait<1>();
@@ -1810,6 +1814,10 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 	const float* pa = rsf + ua;
 	const float* pb = rsf + ub;
 	const bool box_full = __all_sync(0xffffffffu, ub - ua == K); /* false only for the strips at the left/right image edge */
+	/* L2 prefetch plan: the strip's RS columns span two 128-byte lines per row; lanes 0..D-1 take the first line of the D
+	 * rows of a group, lanes 16..16+D-1 the second */
+	const int pf_row = lane & 15;
+	const float* pf = rsf + (clampi(xs - LO + 1 + 32 * (lane >> 4), 0, w - 1) + pf_row * w);
 	float* pc = circf + (x_in ? x : 0);
 
 	float la[D], lb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D];
@@ -1869,11 +1877,8 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
 		}
 		if (g + 1 < n_groups)
 			load_group(t + D);
-		if (INNER && t + 3 * D <= h) { /* pull the group after the next one into L2: its loads then see L2, not DRAM latency */
-#pragma unroll
-			for (int s = 0; s < D; s++)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(elem_ptr(pa, (unsigned)((t + 2 * D + s) * w))));
-		}
+		if (INNER && t + 3 * D <= h && pf_row < D) /* pull the group after the next one into L2 with ONE instruction: lane = (row, line) */
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(elem_ptr(pf, (unsigned)((t + 2 * D) * w))));
 
 		constexpr int DD = 4 * D;
 		const int y0 = t - R; /* circularity row of step 0 */

@@ -1300,15 +1300,23 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
 				static const size_t hoist_pad = getenv("VP_HOIST_PAD") ? (size_t)atoi(getenv("VP_HOIST_PAD")) : 0; /* tuning aid: caps residency */
 				const size_t HOIST_SMEM_L = HOIST_SMEM + hoist_pad;
+				static const int hoist_px = getenv("VP_HOIST_PX") ? atoi(getenv("VP_HOIST_PX")) : 4; /* tuning aid: pixels per thread */
 				if (!ctx->hoist_attr) {
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
+					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
 					ctx->hoist_attr = true;
 				}
-				if (p->fmt == VP_FMT_RGGB8)
-					k_reproject_hoist<FMT_RGGB><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				if (hoist_px == 2) {
+					if (p->fmt == VP_FMT_RGGB8)
+						k_reproject_hoist<FMT_RGGB, 2><<<grid, 512, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+					else
+						k_reproject_hoist<FMT_GRBG, 2><<<grid, 512, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				} else if (p->fmt == VP_FMT_RGGB8)
+					k_reproject_hoist<FMT_RGGB, 4><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 				else
-					k_reproject_hoist<FMT_GRBG><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+					k_reproject_hoist<FMT_GRBG, 4><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 				rc = check_launch(ctx, "k_reproject_hoist");
 			} else if (staged) {
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), g);
