@@ -299,3 +299,37 @@ def test_full_size_with_host_derived_parameters(ctx, port):
     common.assert_float_images_equal(got["circ"], want["circ"])
     check_frame(got, 0, want)
     assert want["counter"][0] >= 60
+
+
+def test_full_size_batch_through_the_four_frame_reprojection(ctx, port):
+    """Six distinct 2448x2048 frames in one device-resident batch: the automatic chunk is 4, so the byte-packed four-frame
+    reprojection runs a full quad and a partial one (two frames); every frame's flat image and blob list against the oracle."""
+    from vpb200 import geometry as G, synth as S
+    wq, hq = 1224, 1024
+    cam = G.default_camera(wq, hq, k2=0.05)
+    persp = G.Perspective(cam)
+    persp.geometry_check(wq, hq, 180.0)
+    lp = G.launch_params(persp, 0, wq, hq)
+    p = common.to_vpo(lp)
+    vp = common.to_vp(p)
+    scene = S.random_scene(persp.visible_field_extent, 12, 3, seed=9)
+    clean = S.render_rgb(scene, cam, 2 * wq, 2 * hq)
+    frames = [S.render_raw(scene, cam, 2 * wq, 2 * hq, S.FMT_RGGB, seed=100 + i, clean_rgb=clean).reshape(-1) for i in range(6)]
+    n, nf, rb = len(frames), p.wf * p.hf, frames[0].size
+    bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
+    ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                            bufs["m"].device_ptr, bufs["c"].device_ptr)
+    flat = bufs["flat"].read(np.uint8).reshape(n, p.hf, p.wf, 4)
+    circ = bufs["circ"].read(np.float32).reshape(n, p.hf, p.wf)
+    counter = bufs["c"].read(np.int32).reshape(n, 3)
+    m = bufs["m"].read(np.uint8).reshape(n, vp.max_blobs, 22)
+    for i in (0, 3, 4, 5):
+        want = port.detect(frames[i], p)
+        np.testing.assert_array_equal(flat[i], want["flat"])
+        common.assert_float_images_equal(circ[i], want["circ"])
+        np.testing.assert_array_equal(counter[i], want["counter"])
+        k = min(int(counter[i, 0]), vp.max_blobs)
+        common.assert_matches_equal(m[i, :k].copy().view(lib.MATCH_DTYPE).reshape(-1), want["matches"])
+    for b in bufs.values():
+        b.release()

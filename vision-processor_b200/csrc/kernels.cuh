@@ -849,6 +849,262 @@ __global__ void __launch_bounds__(1024 / PX, 2) k_reproject_hoist(const uint8_t*
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * K1, four frames at a time (the default of the batched path).
+ *
+ * k_reproject_hoist is bounded by the shared-memory pipe: 16 fp32 tap loads per pixel and frame.  The weights and the tap
+ * addresses are the same for every frame of the camera, so the staged planes here hold, per texel, the BYTES OF FOUR
+ * FRAMES in one 32-bit word: one LDS fetches a tap for four frames, two PRMT turn a byte pair into the biased floats
+ * 2^23 + b, and one FFMA2 with broadcast operands forms the two products (frame A, frame B) x the scalar weight.  Per pixel and frame: 4 LDS instead of 16, the staging does no arithmetic at all (a byte transpose
+ * of the four frames' raw vectors: 2 PRMT per staged word) and stores a quarter of the bytes.  The arithmetic per frame is
+ * unchanged -- same operations in the same order on the same values: bit-identical to k_reproject_hoist.
+ *
+ * Pipeline per quad of frames: copy(q+1) in flight (cp.async, own vectors) | convert(q) -> T | barrier | blend(q) | barrier.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr size_t HOIST4_SMEM = (size_t)HT * 4 + 2 * 4 * (size_t)HRING;
+
+/* w * (byte LO, byte LO+1) of a staged word as ONE packed FMA on the biased floats 2^23 + b (0x4B0000bb):
+ * fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once, i.e. bit for bit mul.rn(w, float(b)); wm = -w * 2^23
+ * is exact (a power-of-two scaling) */
+template <int LO>
+__device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w, float wm)
+{
+	const float2 b = make_float2(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7440 + LO)), __uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7441 + LO)));
+	unsigned long long r;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(b)), "l"(f2_bits(make_float2(w, w))), "l"(f2_bits(make_float2(wm, wm))));
+	return bits_f2(r);
+}
+
+template <int FMT, bool FULL>
+__device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][8], const int (&O)[4][4], uint32_t* __restrict__ out,
+                                             uint32_t nfl, int wf, bool okx, int rows_ok, int n_valid, unsigned long long one2)
+{
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		float2 ab[4], cd[4]; /* channel c: (frame A, frame B) and (frame C, frame D) */
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			const uint32_t* t = T + O[k][c];
+			/* weights of channel c: W[k][4*(c>>1) + tap] holds (channel 2*(c>>1), channel 2*(c>>1)+1) */
+#pragma unroll
+			for (int tap = 0; tap < 4; tap++) {
+				const uint32_t wd = t[(tap & 1) + (tap >> 1) * HP];
+				const float2 wp = W[k][4 * (c >> 1) + tap];
+				const float w = (c & 1) ? wp.y : wp.x;
+				const float wm = __fmul_rn(w, -8388608.0f);
+				const float2 pab = weighted_pair<0>(wd, w, wm);
+				const float2 pcd = weighted_pair<2>(wd, w, wm);
+				/* ((p00 + p10) + p01) + p11, every sum rounded on its own */
+				ab[c] = tap == 0 ? pab : add2_opaque(pab, ab[c], one2);
+				cd[c] = tap == 0 ? pcd : add2_opaque(pcd, cd[c], one2);
+			}
+			ab[c] = add2(ab[c], make_float2(8388608.0f, 8388608.0f)); /* RNE to integer in the mantissa */
+			cd[c] = add2(cd[c], make_float2(8388608.0f, 8388608.0f));
+		}
+		uint32_t* o = out + (uint32_t)(4 * k) * (uint32_t)wf;
+		const bool in = FULL || (okx && 4 * k < rows_ok);
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			uint32_t v[4];
+#pragma unroll
+			for (int c = 0; c < 4; c++)
+				v[c] = __float_as_uint(j == 0 ? ab[c].x : j == 1 ? ab[c].y : j == 2 ? cd[c].x : cd[c].y);
+			const uint32_t px = FMT == FMT_RGGB ? drgb_biased(v[0], (v[1] >> 1) + (v[2] >> 1), v[3]) : drgb_biased(v[1], (v[0] >> 1) + (v[3] >> 1), v[2]);
+			if (in && j < n_valid)
+				o[(size_t)j * nfl] = px;
+		}
+	}
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+                                                               const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq,
+                                                               int wf, int hf, int n_frames, int chunk, float one)
+{
+	extern __shared__ __align__(16) unsigned char hoist_smem[];
+	uint32_t* const T = reinterpret_cast<uint32_t*>(hoist_smem);
+	unsigned char* const ring = hoist_smem + (size_t)HT * 4;
+	const int tx = blockIdx.x, ty = blockIdx.y;
+	const int f0 = blockIdx.z * chunk;
+	const int n = min(n_frames, f0 + chunk) - f0;
+	const TileEntry e = table[ty * gridDim.x + tx];
+	const int tid = threadIdx.x;
+	const int lx = tid & 63, ly = tid >> 6;
+	const int gx = tx * FT_W + lx;
+	const uint32_t nfl = (uint32_t)wf * (uint32_t)hf;
+	const uint8_t* const raw = raw0 + (size_t)f0 * frame_stride;
+	float2 pos[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gy = ty * FT_H + ly + 4 * k;
+		pos[k] = make_float2(0.f, 0.f);
+		if (gx < wf && gy < hf)
+			pos[k] = __ldg(lut + (gy * wf + gx));
+	}
+
+	if (!(e.flags & 1)) { /* footprint does not fit: direct gather, frame by frame */
+#pragma unroll 1
+		for (int f = 0; f < n; f++) {
+			const uint8_t* rawf = raw + (size_t)f * frame_stride;
+			uint32_t* out = flat + (size_t)(f0 + f) * nfl;
+#pragma unroll 1
+			for (int k = 0; k < 4; k++) {
+				const int gy = ty * FT_H + ly + 4 * k;
+				if (gx < wf && gy < hf) {
+					const float2 q = __ldg(lut + (gy * wf + gx));
+					uint32_t v;
+					if (fabsf(q.x) < 1048576.0f && fabsf(q.y) < 1048576.0f) {
+						v = reproject_bayer_rte_fast<FMT>(rawf, wq, hq, q.x, q.y);
+					} else {
+						uint32_t r, g, b;
+						const SrcBayer s{ rawf, 2 * wq };
+						demosaic<FMT, MODE_RTE>(s, wq, hq, q.x, q.y, r, g, b);
+						v = drgb(r, g, b);
+					}
+					out[gy * wf + gx] = v;
+				}
+			}
+		}
+		return;
+	}
+
+	/* ---- frame-invariant staging plan: up to two 16-byte raw vectors per thread and frame ---- */
+	const int row_bytes = 2 * wq;
+	const bool vec = (e.flags & 2) != 0;
+	const int n_rr = 2 * e.height;
+	int s_src[2], s_dst[2], s_edge[2]; /* s_edge < 0: no vector */
+#pragma unroll
+	for (int i = 0; i < 2; i++) {
+		const int v = tid + 256 * i;
+		const int q4 = v / (4 * HNV), w = v - q4 * (4 * HNV);
+		const int half = w >= 2 * HNV ? 1 : 0, w2 = w - half * 2 * HNV;
+		const int cv = w2 >> 1, rr = 4 * q4 + half + 2 * (w2 & 1);
+		s_src[i] = 0;
+		s_dst[i] = 0;
+		s_edge[i] = -1;
+		if (vec && rr < n_rr) {
+			const int qy = clampi(e.jb + (rr >> 1), 0, hq - 1);
+			const int qx0 = e.ib + cv * 8;
+			const int qxc = clampi(qx0, 0, wq - 8);
+			s_src[i] = (2 * qy + (rr & 1)) * row_bytes + 2 * qxc;
+			s_dst[i] = (rr & 1) * 2 * HPLANE + (rr >> 1) * HP + cv * 8;
+			s_edge[i] = qx0 < 0 ? 1 : (qx0 != qxc ? 2 : 0);
+		}
+	}
+	unsigned char* const my_ring = ring + tid * 16; /* frame j, vector i of stage st: my_ring + (st*4 + j)*HRING + i*4096 */
+	const int n_quads = (n + 3) >> 2;
+	const uint8_t* next_src = raw; /* first frame of the next quad to copy */
+	auto issue_copy = [&](int q) { /* frames 4q..4q+3 (the last frame repeated past the end) into stage q & 1; always commits */
+		if (vec && q < n_quads) {
+			unsigned char* dst = my_ring + (q & 1) * 4 * HRING;
+			const int left = n - 4 * q; /* >= 1 */
+			const uint8_t* src = next_src;
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+#pragma unroll
+				for (int i = 0; i < 2; i++)
+					if (s_edge[i] >= 0)
+						cp_async16(dst + j * HRING + i * 4096, src + s_src[i]);
+				if (j + 1 < left)
+					src += frame_stride;
+			}
+			next_src += 4 * frame_stride;
+		}
+		cp_async_commit();
+	};
+	auto convert = [&](int q) { /* this thread's vectors of quad q: byte transpose of the four frames -> T */
+		if (vec) {
+#pragma unroll
+			for (int i = 0; i < 2; i++) {
+				if (s_edge[i] < 0)
+					continue;
+				uint32_t fr[4][4];
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					uint4 qq = *reinterpret_cast<const uint4*>(my_ring + ((q & 1) * 4 + j) * HRING + i * 4096);
+					if (s_edge[i]) { /* replicate the edge quad's two bytes over the whole vector */
+						const uint32_t eq = s_edge[i] == 1 ? (qq.x & 0xFFFFu) : (qq.w >> 16);
+						qq.x = qq.y = qq.z = qq.w = eq * 0x00010001u;
+					}
+					fr[j][0] = qq.x; fr[j][1] = qq.y; fr[j][2] = qq.z; fr[j][3] = qq.w;
+				}
+				uint32_t pe[8], po[8]; /* plane 2s (even bytes) and 2s+1 (odd bytes), 8 texels each, byte j of a word = frame j */
+#pragma unroll
+				for (int w = 0; w < 4; w++) {
+					const uint32_t ab_lo = __byte_perm(fr[0][w], fr[1][w], 0x5140), ab_hi = __byte_perm(fr[0][w], fr[1][w], 0x7362);
+					const uint32_t cd_lo = __byte_perm(fr[2][w], fr[3][w], 0x5140), cd_hi = __byte_perm(fr[2][w], fr[3][w], 0x7362);
+					pe[2 * w] = __byte_perm(ab_lo, cd_lo, 0x5410);     /* byte 0 of the four frames */
+					po[2 * w] = __byte_perm(ab_lo, cd_lo, 0x7632);     /* byte 1 */
+					pe[2 * w + 1] = __byte_perm(ab_hi, cd_hi, 0x5410); /* byte 2 */
+					po[2 * w + 1] = __byte_perm(ab_hi, cd_hi, 0x7632); /* byte 3 */
+				}
+				uint32_t* d0 = T + s_dst[i];
+				uint32_t* d1 = d0 + HPLANE;
+				reinterpret_cast<uint4*>(d0)[0] = make_uint4(pe[0], pe[1], pe[2], pe[3]);
+				reinterpret_cast<uint4*>(d0)[1] = make_uint4(pe[4], pe[5], pe[6], pe[7]);
+				reinterpret_cast<uint4*>(d1)[0] = make_uint4(po[0], po[1], po[2], po[3]);
+				reinterpret_cast<uint4*>(d1)[1] = make_uint4(po[4], po[5], po[6], po[7]);
+			}
+		} else { /* raw rows not 16-byte aligned (wq % 8 != 0): per-texel gather with the edge replicated */
+			const int tot = 4 * e.height * TQ_W;
+			for (int v = tid; v < tot; v += 256) {
+				const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
+				const int jj = rc >> 2, c = rc & 3;
+				const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
+				const int o = (2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1);
+				uint32_t wd = 0;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					wd |= (uint32_t)__ldg(raw + (size_t)min(4 * q + j, n - 1) * frame_stride + o) << (8 * j);
+				T[c * HPLANE + jj * HP + ii] = wd;
+			}
+		}
+	};
+	issue_copy(0);
+
+	/* ---- frame-invariant part: weights and tap offsets of this thread's four pixels (the first copy is in flight) ---- */
+	float2 W[4][8];
+	int O[4][4];
+	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int gy = ty * FT_H + ly + 4 * k;
+		const bool ok = gx < wf && gy < hf;
+		int ixp, ixn, iyp, iyn;
+		float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
+		axis_staged2(add2(make_float2(pos[k].x, pos[k].x), make_float2(0.25f, -0.25f)), xmagic, ixp, ixn, ax, ox);
+		axis_staged2(add2(make_float2(pos[k].y, pos[k].y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
+		const float2 ayp = make_float2(ay.x, ay.x), oyp = make_float2(oy.x, oy.x);
+		const float2 ayn = make_float2(ay.y, ay.y), oyn = make_float2(oy.y, oy.y);
+		W[k][0] = mul2(ox, oyp); W[k][1] = mul2(ax, oyp); W[k][2] = mul2(ox, ayp); W[k][3] = mul2(ax, ayp);
+		W[k][4] = mul2(ox, oyn); W[k][5] = mul2(ax, oyn); W[k][6] = mul2(ox, ayn); W[k][7] = mul2(ax, ayn);
+		O[k][0] = ok ? iyp * HP + ixp : 0; /* pixels outside the image read texel 0 and are not stored */
+		O[k][1] = ok ? HPLANE + iyp * HP + ixn : 0;
+		O[k][2] = ok ? 2 * HPLANE + iyn * HP + ixp : 0;
+		O[k][3] = ok ? 3 * HPLANE + iyn * HP + ixn : 0;
+	}
+	const bool okx = gx < wf;
+	const int rows_ok = hf - (ty * FT_H + ly);
+	const bool full = (tx + 1) * FT_W <= wf && (ty + 1) * FT_H <= hf;
+	uint32_t* out = flat + (size_t)f0 * nfl + ((uint32_t)(ty * FT_H + ly) * (uint32_t)wf + (uint32_t)gx);
+	const unsigned long long one2 = f2_bits(make_float2(one, one));
+
+#pragma unroll 1
+	for (int q = 0; q < n_quads; q++) {
+		issue_copy(q + 1);
+		cp_async_wait<1>(); /* quad q has landed (this thread's vectors) */
+		convert(q);
+		__syncthreads();
+		const int n_valid = min(4, n - 4 * q);
+		if (full)
+			hoist4_blend<FMT, true>(T, W, O, out, nfl, wf, true, 16, n_valid, one2);
+		else
+			hoist4_blend<FMT, false>(T, W, O, out, nfl, wf, okx, rows_ok, n_valid, one2);
+		out += (size_t)4 * nfl;
+		__syncthreads(); /* everybody has read T before the next quad is converted into it */
+	}
+}
+
+/* ------------------------------------------------------------------------------------------------
  * raw2quad.cl:21-39 (stage API only; the fused path never materialises the planes)
  * ---------------------------------------------------------------------------------------------- */
 __global__ void k_raw2quad_bayer(const uint8_t* __restrict__ raw, uint8_t* __restrict__ c0, uint8_t* __restrict__ c1,

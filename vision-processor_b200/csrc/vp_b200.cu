@@ -87,6 +87,7 @@ struct vp_ctx {
 	bool fused_sat = false; /* measured slower than row scan + column scan on B200 (profiles/r01_fused_sat_sweep.txt); kept as an A/B option */
 	bool grad_sat_attr = false;
 	bool hoist_attr = false;
+	bool hoist4_attr = false;
 	volatile float one = 1.0f; /* handed to kernels that need a 1.0 the compiler cannot fold (add2_opaque) */
 	int32_t* agg[MAX_LANES_DECL] = {};  /* strip aggregates of k_grad_sat, per lane */
 	size_t agg_words = 0;
@@ -1308,7 +1309,18 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
 					ctx->hoist_attr = true;
 				}
-				if (hoist_px == 2) {
+				static const int hoist_quads = getenv("VP_HOIST_QUADS") ? atoi(getenv("VP_HOIST_QUADS")) : 1; /* tuning aid / A-B */
+				if (hoist_px == 4 && hoist_quads && chunk >= 4) {
+					if (!ctx->hoist4_attr) {
+						CK(ctx, cudaFuncSetAttribute(k_reproject_hoist4<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST4_SMEM));
+						CK(ctx, cudaFuncSetAttribute(k_reproject_hoist4<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST4_SMEM));
+						ctx->hoist4_attr = true;
+					}
+					if (p->fmt == VP_FMT_RGGB8)
+						k_reproject_hoist4<FMT_RGGB><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+					else
+						k_reproject_hoist4<FMT_GRBG><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				} else if (hoist_px == 2) {
 					if (p->fmt == VP_FMT_RGGB8)
 						k_reproject_hoist<FMT_RGGB, 2><<<grid, 512, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 					else
