@@ -1203,7 +1203,9 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
 	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
-	const int seg = seg_env > 0 ? seg_env : 128; /* rows per CTA of the streaming circularity kernels */
+	/* rows per CTA of the streaming circularity kernels: 128 for batches (few halo rows per segment); a lone frame has only
+	 * hf/128 x 14 CTAs to offer, so shorter segments trade halo work for shorter dependent chains and a full GPU */
+	const int seg = seg_env > 0 ? seg_env : (n_frames >= 3 ? 128 : 32);
 	const int n_seg = cdiv(hf, seg);
 	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
 	if (sat_free) {
