@@ -8,7 +8,7 @@ import os
 import subprocess
 import sys
 
-STAGE = {"k_reproject_hoist": "reproject", "k_reproject_staged": "reproject", "k_grad_rowscan": "grad_rowscan", "k_colscan": "colscan",
+STAGE = {"k_reproject_hoist4": "reproject", "k_reproject_hoist": "reproject", "k_reproject_staged": "reproject", "k_grad_rowscan": "grad_rowscan", "k_colscan": "colscan",
          "k_circ_stream_rs": "circ_peaks", "k_peaks_emit": "peaks_emit", "k_sat_check_fix": "sat_check", "k_peaks_prepare": "prepare"}
 frames, reps = float(sys.argv[1]), sys.argv[2:]
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
