@@ -155,7 +155,7 @@ def run_reference(args, rank: int):
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
     sample = f"{per_step} frames per step ({kind}: " + ("reference kernel/*.cl compiled in place via oracle/clemu.h" if kind == "reference" else "oracle/vp_oracle.c") + f"), {cores} OpenMP threads"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32",
         "data": "synthetic", "config": {"workload": "single camera 2448x2048 BayerRG8 full detection pipeline", "frames_per_step": per_step},
@@ -166,7 +166,26 @@ def run_reference(args, rank: int):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner at the first
+    collective, for one) is sent to stderr by pointing fd 1 at fd 2; the result goes to the saved descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -355,7 +374,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(lp, frames)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     pin_raw.free(); pin_m.free(); pin_c.free()
     ctx.close()
     if world > 1:
