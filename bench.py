@@ -210,6 +210,10 @@ def main():
     import torch.distributed as dist
     from vpb200 import lib
 
+    numa_cpus = []
+    if world > 1:  # one camera stream per GPU: keep this rank's pinned frame ring on the socket its GPU hangs off
+        from vpb200 import shard
+        numa_cpus = shard.bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -360,7 +364,8 @@ def main():
         "config": {"workload": "single camera 2448x2048 BayerRG8 full detection pipeline (BASELINE configs[1]); one camera stream per GPU",
                    "frames_per_step_per_gpu": B, "flat_size": [lp.wf, lp.hf], "max_blobs": p.max_blobs, "blobs_per_frame": blobs_per_frame,
                    "l2": f"inputs larger than L2: {B} frames x {rb} B = {B * rb / 1e6:.0f} MB raw per step, streamed from HBM every step",
-                   "parallelism": f"{world} independent camera streams, no collective"},
+                   "parallelism": f"{world} independent camera streams, no collective",
+                   "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else "all"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Be * rb, "d2h_bytes_per_step": Be * (p.max_blobs * 22 + 12),
                 "frames_per_step": Be, "steps": e2e_steps},

@@ -68,3 +68,24 @@ def aggregate_throughput(items_this_rank: int, elapsed_s_this_rank: float, devic
     total = sum_over_ranks(float(items_this_rank), device)
     worst = max_over_ranks(float(elapsed_s_this_rank), device)
     return total / worst if worst > 0 else float("inf")
+
+
+def bind_to_gpu_numa_node(gpu_index: int) -> list:
+    """Pin this process to the CPUs next to its GPU (NVML's affinity mask) BEFORE it allocates pinned host memory, so that
+    the frame ring of camera c lives on the socket GPU c hangs off -- with eight cameras uploading 5 MB frames at once the
+    host-to-device path is otherwise limited by cross-socket traffic.  The reference gets the same effect from running one
+    OS process per camera.  Returns the CPU list, or [] when NVML is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return []
