@@ -241,6 +241,24 @@ VP_API int vp_detect_images(vp_ctx* ctx, const uint8_t** d_flat, const float** d
  * recomputed in the reference's sequential summation order */
 VP_API int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n);
 
+/* ---- blob list -> hypothesis hand-off ------------------------------------------------------------
+ * struct Match, src/blobs/match.h:22-30 (Eigen::Vector2f pos; Vector3i color, center; float circ, score): 40 bytes */
+typedef struct {
+	float pos[2];      /* field millimetres: Perspective::flat2field(match.x, match.y), main.cpp:303 */
+	int32_t color[3];
+	int32_t center[3];
+	float circ, score;
+} vp_field_match;
+/* What src/main.cpp:297-325 does per frame on the CPU (copy into `Match` records, KD-tree insert), for a whole batch on the
+ * device: d_out[f][i] = record of blob i (i < min(counter[3f], max_blobs), list order kept), and a uniform grid of
+ * cell_mm x cell_mm cells over the visible extent starting at (off_x, off_y) instead of the tree: d_order[f][k] = blob
+ * indices sorted by (cell, index), d_cell_start[f][c] = first k of cell c (cells_x*cells_y + 1 entries per frame; cells
+ * are row-major, positions outside the grid -- and NaN positions of plateau peaks -- are clamped into it).  A radius
+ * search visits the cells the disc overlaps.  max_blobs <= 4096. */
+VP_API int vp_blobs_to_field_device(vp_ctx* ctx, const vp_match* d_matches, const int32_t* d_counter, int n_frames, int max_blobs, float field_scale,
+                                    float off_x, float off_y, float cell_mm, int cells_x, int cells_y, vp_field_match* d_out, int32_t* d_order,
+                                    int32_t* d_cell_start);
+
 /* debug-stream conversions straight from a raw frame / detection images (device pointers), Resources.cpp:166-186 */
 VP_API int vp_raw2nv12_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_nv12, int sample_mode);
 VP_API int vp_raw2rgba_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int hq, uint8_t* d_rgba, int sample_mode);

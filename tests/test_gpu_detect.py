@@ -333,3 +333,50 @@ def test_full_size_batch_through_the_four_frame_reprojection(ctx, port):
         common.assert_matches_equal(m[i, :k].copy().view(lib.MATCH_DTYPE).reshape(-1), want["matches"])
     for b in bufs.values():
         b.release()
+
+
+def test_blobs_to_field_records_and_cell_lists(ctx, port):
+    """the CPU loop of main.cpp:297-325 (CLMatch -> Match in field millimetres, spatial index) on the device for
+    a batch: records bit-exact against flat2field on the host, the cell lists against a stable sort by (cell, index);
+    frames with zero blobs, with an overflowing counter and with NaN positions (plateau peaks) included."""
+    frames, lists, counters = [], [], []
+    cases = [dict(wq=160, hq=120, n_robots=3, n_balls=3, seed=2), dict(wq=160, hq=120, frame="noise", seed=9, max_blobs=300),
+             dict(wq=160, hq=120, n_robots=0, n_balls=0, seed=4, thr=1e9)]
+    max_blobs = 300
+    for kw in cases:
+        kw = dict(kw, max_blobs=max_blobs)
+        p, raw, _ = common.make_case(**kw)
+        w = port.detect(raw, p, want_images=False)
+        rec = np.zeros(max_blobs, lib.MATCH_DTYPE)
+        rec[:len(w["matches"])] = w["matches"]
+        lists.append(rec)
+        counters.append(w["counter"])
+    plateau = np.zeros(max_blobs, lib.MATCH_DTYPE)   # hand-made list: NaN offsets, positions outside the grid
+    plateau["x"][:4] = [np.nan, -50.0, 1e6, 17.25]
+    plateau["y"][:4] = [3.0, np.nan, -1e6, 40.5]
+    lists.append(plateau)
+    counters.append(np.array([4, 0, 0], np.int32))
+    matches, counters = np.stack(lists), np.stack(counters)
+    assert counters[1, 0] > max_blobs and counters[2, 0] == 0
+    scale, ox, oy, cell = np.float32(p.field_scale), np.float32(p.off_x), np.float32(p.off_y), np.float32(150.0)
+    cx, cy = 6, 5
+    rec, order, cs = ctx.blobs_to_field(matches, counters, max_blobs, float(scale), float(ox), float(oy), float(cell), cx, cy)
+    for f in range(len(counters)):
+        n = min(int(counters[f, 0]), max_blobs)
+        m = matches[f, :n]
+        pos = np.stack([m["x"] * scale + ox, m["y"] * scale + oy], -1).astype(np.float32)       # Perspective.cpp:127-129
+        common.assert_float_images_equal(rec[f, :n]["pos"], pos)        # bit-exact; NaN by class (payloads are platform-specific)
+        np.testing.assert_array_equal(rec[f, :n]["color"], m["color"].astype(np.int32))
+        np.testing.assert_array_equal(rec[f, :n]["center"], m["center"].astype(np.int32))
+        np.testing.assert_array_equal(rec[f, :n]["circ"].view(np.uint32), m["circ"].view(np.uint32))
+        np.testing.assert_array_equal(rec[f, :n]["score"].view(np.uint32), m["score"].view(np.uint32))
+        with np.errstate(invalid="ignore"):
+            ix = np.floor((pos[:, 0] - ox) / cell)
+            iy = np.floor((pos[:, 1] - oy) / cell)
+        ix = np.where(ix >= 0, np.minimum(ix, cx - 1), 0).astype(np.int64)      # NaN compares false -> cell 0
+        iy = np.where(iy >= 0, np.minimum(iy, cy - 1), 0).astype(np.int64)
+        cells = iy * cx + ix
+        want_order = np.argsort(cells, kind="stable")
+        np.testing.assert_array_equal(order[f, :n], want_order)
+        want_cs = np.searchsorted(cells[want_order], np.arange(cx * cy + 1), side="left")
+        np.testing.assert_array_equal(cs[f], want_cs)

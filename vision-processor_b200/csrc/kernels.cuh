@@ -2479,4 +2479,79 @@ __global__ void __launch_bounds__(256) k_quad2rgba(Src s, uint32_t* __restrict__
 	out[(size_t)y * wq + x] = r | (g << 8) | (b << 16) | 0xFF000000u; /* quad2rgba.cl:52 */
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Blob list -> hypothesis hand-off: what src/main.cpp:297-325 does on the CPU per frame -- copy every
+ * CLMatch into a `Match` with its position in field millimetres (Perspective::flat2field, Perspective.cpp:127-129) and
+ * insert it into a KD-tree for the radius searches of src/blobs -- done per batch on the GPU: the 40-byte records come
+ * out ready to use, plus a uniform grid over the visible field (cell list by counting order) in place of the tree:
+ *   order[k]      blob indices sorted by (cell, index): cells in row-major order, raster order inside a cell
+ *   cell_start[c] first k of cell c (n_cells + 1 entries)
+ * One CTA per frame; up to FB_MAX blobs are ordered by a bitonic sort of the unique keys cell * FB_MAX + index.
+ * ---------------------------------------------------------------------------------------------- */
+constexpr int FB_MAX = 4096;
+__global__ void __launch_bounds__(256) k_blobs_to_field(const uint8_t* __restrict__ matches, size_t match_frame_stride, const int32_t* __restrict__ counter,
+                                                        int max_blobs, float scale, float off_x, float off_y, float cell_mm, int cells_x, int cells_y,
+                                                        vp_field_match* __restrict__ out, int32_t* __restrict__ order, int32_t* __restrict__ cell_start)
+{
+	__shared__ uint32_t key[FB_MAX];
+	const int f = blockIdx.x, tid = threadIdx.x;
+	const int n = min(max(counter[3 * f], 0), max_blobs); /* main.cpp:301 */
+	const int n_cells = cells_x * cells_y;
+	const uint8_t* src = matches + (size_t)f * match_frame_stride;
+	vp_field_match* dst = out + (size_t)f * max_blobs;
+	int n_sort = 1;
+	while (n_sort < n) n_sort <<= 1;
+	for (int i = tid; i < n_sort; i += 256) {
+		uint32_t k = 0xFFFFFFFFu;
+		if (i < n) {
+			const uint8_t* m = src + 22 * (size_t)i; /* CLMatch, main.cpp:33-41: floats at unaligned offsets */
+			uint32_t w[6];
+#pragma unroll
+			for (int j = 0; j < 11; j += 2)
+				w[j >> 1] = (uint32_t)m[2 * j] | ((uint32_t)m[2 * j + 1] << 8) | ((uint32_t)m[2 * j + 2] << 16) | ((uint32_t)m[2 * j + 3] << 24);
+			/* bytes 0-3 x, 4-7 y, 8-10 color, 11-13 center, 14-17 circ, 18-21 score */
+			const float x = __uint_as_float(w[0]), y = __uint_as_float(w[1]);
+			vp_field_match r;
+			r.pos[0] = __fadd_rn(__fmul_rn(x, scale), off_x); /* flat2field: pos * fieldScale + (extent[0], extent[2]) */
+			r.pos[1] = __fadd_rn(__fmul_rn(y, scale), off_y);
+			r.color[0] = m[8]; r.color[1] = m[9]; r.color[2] = m[10];
+			r.center[0] = m[11]; r.center[1] = m[12]; r.center[2] = m[13];
+			r.circ = __uint_as_float((uint32_t)m[14] | ((uint32_t)m[15] << 8) | ((uint32_t)m[16] << 16) | ((uint32_t)m[17] << 24));
+			r.score = __uint_as_float((uint32_t)m[18] | ((uint32_t)m[19] << 8) | ((uint32_t)m[20] << 16) | ((uint32_t)m[21] << 24));
+			dst[i] = r;
+			/* cell of the blob inside the visible extent; NaN positions (plateau peaks, blobList.cl:93-94) go to cell 0 */
+			const float cxf = floorf(__fdiv_rn(__fsub_rn(r.pos[0], off_x), cell_mm)), cyf = floorf(__fdiv_rn(__fsub_rn(r.pos[1], off_y), cell_mm));
+			const int cx = cxf >= 0.f ? (cxf < (float)cells_x ? (int)cxf : cells_x - 1) : 0;
+			const int cy = cyf >= 0.f ? (cyf < (float)cells_y ? (int)cyf : cells_y - 1) : 0;
+			k = (uint32_t)(cy * cells_x + cx) * (uint32_t)FB_MAX + (uint32_t)i;
+		}
+		key[i] = k;
+	}
+	__syncthreads();
+	for (int size = 2; size <= n_sort; size <<= 1) {
+		for (int stride = size >> 1; stride > 0; stride >>= 1) {
+			for (int t = tid; t < (n_sort >> 1); t += 256) {
+				const int lo = 2 * t - (t & (stride - 1)), hi = lo + stride;
+				const bool up = (lo & size) == 0;
+				const uint32_t a = key[lo], b = key[hi];
+				if ((a > b) == up) {
+					key[lo] = b;
+					key[hi] = a;
+				}
+			}
+			__syncthreads();
+		}
+	}
+	int32_t* ord = order + (size_t)f * max_blobs;
+	int32_t* cs = cell_start + (size_t)f * (n_cells + 1);
+	for (int k = tid; k <= n; k += 256) {
+		const int c_here = k < n ? (int)(key[k] / FB_MAX) : n_cells;   /* cell of sorted position k; the end sentinel closes the table */
+		const int c_prev = k > 0 ? (int)(key[k - 1] / FB_MAX) : -1;
+		if (k < n)
+			ord[k] = (int)(key[k] % FB_MAX);
+		for (int c = c_prev + 1; c <= c_here; c++)
+			cs[c] = k;
+	}
+}
+
 } /* namespace vpk */

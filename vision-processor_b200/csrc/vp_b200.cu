@@ -1469,6 +1469,20 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	return VP_OK;
 }
 
+int vp_blobs_to_field_device(vp_ctx* ctx, const vp_match* d_matches, const int32_t* d_counter, int n_frames, int max_blobs, float field_scale, float off_x,
+                             float off_y, float cell_mm, int cells_x, int cells_y, vp_field_match* d_out, int32_t* d_order, int32_t* d_cell_start)
+{
+	REQUIRE(ctx, ctx && d_counter && d_out && d_order && d_cell_start && (d_matches || max_blobs == 0), "null argument");
+	REQUIRE(ctx, n_frames >= 0 && max_blobs >= 0 && max_blobs <= FB_MAX, "max_blobs must be in [0, %d]", FB_MAX);
+	REQUIRE(ctx, cell_mm > 0.f && cells_x > 0 && cells_y > 0 && (long long)cells_x * cells_y <= (1 << 19), "bad grid (cell size must be positive, at most 2^19 cells)");
+	if (n_frames == 0) return VP_OK;
+	CK(ctx, cudaSetDevice(ctx->device));
+	Stage st(ctx, "blobs2field");
+	k_blobs_to_field<<<n_frames, 256, 0, ctx->stream>>>((const uint8_t*)d_matches, (size_t)max_blobs * 22, d_counter, max_blobs, field_scale, off_x, off_y,
+	                                                    cell_mm, cells_x, cells_y, d_out, d_order, d_cell_start);
+	return check_launch(ctx, "k_blobs_to_field");
+}
+
 int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n)
 {
 	REQUIRE(ctx, ctx && n, "null argument");

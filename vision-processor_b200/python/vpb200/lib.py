@@ -26,6 +26,10 @@ MAP_READ, MAP_WRITE, MAP_READWRITE = 1, 2, 3
 
 _NP_OF_FMT = {FMT_RGBA8: (np.uint8, 4), FMT_U8: (np.uint8, 1), FMT_F32: (np.float32, 1)}
 
+# struct Match, src/blobs/match.h:22-30 (vp_field_match): what main.cpp:297-312 builds from every CLMatch
+FIELD_MATCH_DTYPE = np.dtype([("pos", "<f4", 2), ("color", "<i4", 3), ("center", "<i4", 3), ("circ", "<f4"), ("score", "<f4")])
+assert FIELD_MATCH_DTYPE.itemsize == 40
+
 # CLMatch, src/main.cpp:33-41: 22 packed bytes, floats at unaligned offsets 14 and 18
 MATCH_DTYPE = np.dtype({
     "names": ["x", "y", "color", "center", "circ", "score"],
@@ -195,6 +199,7 @@ def load() -> C.CDLL:
         "vp_rgba2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
         "vp_f2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
         "vp_raw2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int]),
+        "vp_blobs_to_field_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
         "vp_copy_to_host": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_copy_to_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
@@ -675,6 +680,26 @@ class Context:
         finally:
             src.release()
             dst.release()
+
+    def blobs_to_field(self, matches: np.ndarray, counters: np.ndarray, max_blobs: int, field_scale: float, off_x: float, off_y: float,
+                       cell_mm: float, cells_x: int, cells_y: int):
+        """main.cpp:297-325 on the device for a batch: matches (n, max_blobs) CLMatch records, counters (n, 3).
+        Returns (records (n, max_blobs) FIELD_MATCH_DTYPE, order (n, max_blobs) i32, cell_start (n, cells+1) i32)."""
+        n = len(counters)
+        m = self.buffer(max(n * max_blobs * 22, 1), np.ascontiguousarray(matches).view(np.uint8).reshape(-1))
+        c = self.buffer(n * 12, np.ascontiguousarray(counters, np.int32).view(np.uint8).reshape(-1))
+        out = self.buffer(max(n * max_blobs * 40, 1))
+        order = self.buffer(max(n * max_blobs * 4, 1))
+        cs = self.buffer(n * (cells_x * cells_y + 1) * 4)
+        try:
+            self._ck(self.lib.vp_blobs_to_field_device(self.h, C.c_void_p(m.device_ptr), C.c_void_p(c.device_ptr), n, max_blobs, field_scale, off_x, off_y,
+                                                       cell_mm, cells_x, cells_y, C.c_void_p(out.device_ptr), C.c_void_p(order.device_ptr),
+                                                       C.c_void_p(cs.device_ptr)))
+            rec = out.read()[:n * max_blobs * 40].view(FIELD_MATCH_DTYPE).reshape(n, max_blobs)
+            return rec, order.read(np.int32)[:n * max_blobs].reshape(n, max_blobs), cs.read(np.int32).reshape(n, cells_x * cells_y + 1)
+        finally:
+            for b in (m, c, out, order, cs):
+                b.release()
 
     def raw2rgba(self, raw: np.ndarray, fmt, wq, hq, mode=0):
         src = self.buffer(raw.nbytes, raw)
