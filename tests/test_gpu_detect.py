@@ -380,3 +380,34 @@ def test_blobs_to_field_records_and_cell_lists(ctx, port):
         np.testing.assert_array_equal(order[f, :n], want_order)
         want_cs = np.searchsorted(cells[want_order], np.arange(cx * cy + 1), side="left")
         np.testing.assert_array_equal(cs[f], want_cs)
+
+
+@pytest.mark.parametrize("scale_mul,dx,dy", [(2.7, 0.0, 0.0), (0.37, 40.0, -25.0), (1.0, -900.0, 300.0), (1.6, 5000.0, 0.0)])
+def test_four_frame_reprojection_on_unusual_geometry(ctx, port, scale_mul, dx, dy):
+    """The byte-packed four-frame kernel on tiles whose footprint does not fit (direct-gather fallback inside the kernel), is
+    tiny, or lies partly/entirely outside the sensor (edge replication in the byte transpose): five frames, chunk 4."""
+    frames = []
+    for s_ in range(5):
+        p, raw, _ = common.make_case(wq=320, hq=200, fmt=s_ % 1, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=30 + s_)
+        frames.append(raw)
+    p.field_scale *= scale_mul
+    p.off_x += dx
+    p.off_y += dy
+    vp = common.to_vp(p)
+    n, nf, rb = len(frames), p.wf * p.hf, frames[0].size
+    bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
+    ctx.set_hoist_chunk(4)
+    try:
+        ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                                bufs["m"].device_ptr, bufs["c"].device_ptr)
+        flat = bufs["flat"].read(np.uint8).reshape(n, p.hf, p.wf, 4)
+        counter = bufs["c"].read(np.int32).reshape(n, 3)
+    finally:
+        ctx.set_hoist_chunk(0)
+    for i in range(n):
+        want = port.detect(frames[i], p)
+        np.testing.assert_array_equal(flat[i], want["flat"])
+        np.testing.assert_array_equal(counter[i], want["counter"])
+    for b in bufs.values():
+        b.release()
