@@ -7,6 +7,7 @@
  */
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -1269,7 +1270,9 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	{
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
-		k_peaks_prepare<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr,
+		/* enough CTAs to clear the blob masks of a lone frame in one pass (the kernel strides over them) */
+		const int prep_ctas = std::max(cdiv(n, 256), std::min(cdiv(n * wpr, 256), 4 * ctx->sm_count));
+		k_peaks_prepare<<<prep_ctas, 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr,
 		                                                       fused_sat ? ctx->sync_words : nullptr, fused_sat ? n_frames * (1 + n_strips) : 0);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
