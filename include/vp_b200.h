@@ -293,6 +293,18 @@ VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
 /* tuning knob of variant 2: frames of a launch group one CTA processes with the same registers (0 = automatic: 8, fewer
  * when the grid would not fill the GPU) */
 VP_API int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames);
+/* latency knob of vp_detect_host with ONE pinned frame (a camera delivering frame by frame, src/main.cpp:262-289): the
+ * upload is cut into `strips` chunks of raw rows (1..16, default 2) and the reprojection of the flat rows a chunk
+ * completes runs while the next chunk is still crossing PCIe; 1 = upload the frame, then compute.  Results are
+ * bit-identical for every value. */
+VP_API int vp_ctx_set_strips(vp_ctx* ctx, int strips);
+/* A/B switch (default on), results are bit-identical: from the second one-frame call of vp_detect_host in an unchanged
+ * configuration (parameters, buffers, knobs) the enqueued sequence -- chunked upload, strip kernels, download -- is
+ * captured once into a CUDA graph and replayed with one launch per frame; frames at other pinned addresses (the
+ * camera's buffer ring) only repoint the upload nodes.  Pageable frames take direct launches. */
+VP_API int vp_ctx_set_latency_graph(vp_ctx* ctx, int on);
+/* one-frame calls of vp_detect_host served by a graph replay so far (tests, tools) */
+VP_API uint64_t vp_latency_graph_replays(const vp_ctx* ctx);
 /* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
  * tiled kernel; results are bit-identical */
 VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);

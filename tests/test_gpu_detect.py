@@ -162,6 +162,107 @@ def test_hoisted_reprojection_over_frame_chunks(ctx, port, chunk, kw):
         b.release()
 
 
+@pytest.mark.parametrize("strips", [1, 2, 5, 16])
+@pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7),
+                                dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=-0.25, n_robots=2, n_balls=1),
+                                dict(wq=160, hq=420, fmt=0, frame="noise", seed=3, thr=15.0)])
+def test_lone_frame_pipelined_with_its_upload(ctx, port, kw, strips):
+    """Latency path: the frame arrives in `strips` chunks of raw rows and reprojection, gradient + row sums and the
+    circularity segments run strip by strip behind them.  Every chunking gives the results of the whole-frame pass."""
+    p, raw, _ = common.make_case(**kw)
+    want = port.detect(raw, p)
+    ctx.set_strips(strips)
+    try:
+        got = ctx.detect(raw, common.to_vp(p), pinned=True)
+    finally:
+        ctx.set_strips(2)
+    np.testing.assert_array_equal(got["flat"], want["flat"])
+    np.testing.assert_array_equal(got["grad"], want["grad"])
+    common.assert_float_images_equal(got["circ"], want["circ"])
+    check_frame(got, 0, want)
+    assert got["sat_fallbacks"] == 0
+
+
+@pytest.mark.parametrize("strips", [3, 16])
+def test_lone_frame_in_strips_with_sat_fallback_and_rolled_camera(ctx, port, strips):
+    """(a) a frame whose row sums leave the exactness bound in a LATE strip, after earlier strips have published blobs:
+    everything published is forgotten and the frame is redone in sequential order; (b) a camera rolled by 180 degrees:
+    the first flat rows need the last raw rows, the schedule degenerates to upload-then-compute."""
+    p, clean, _ = common.make_case(wq=1600, hq=96, scale_mm=4.0, n_robots=3, n_balls=3, seed=3)
+    h, w = 2 * p.hq, 2 * p.wq
+    yy, xx = np.mgrid[0:h, 0:w]
+    stripes = (((xx + yy) // 6) % 2 * 255).astype(np.uint8)
+    late = clean.reshape(h, w).copy()
+    late[h - 40:, :3000] = stripes[h - 40:, :3000]
+    ctx.set_strips(strips)
+    try:
+        want = port.detect(late.reshape(-1), p)
+        got = ctx.detect(late.reshape(-1), common.to_vp(p), pinned=True)
+        assert got["sat_fallbacks"] == 1
+        np.testing.assert_array_equal(got["grad"], want["grad"])
+        common.assert_float_images_equal(got["circ"], want["circ"])
+        check_frame(got, 0, want)
+
+        p2, raw2, _ = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=11)
+        r = np.array(p2.model.r, np.float32).reshape(3, 3)
+        r[0] *= -1.0  # image x and y axes reversed: a roll of 180 degrees about the optical axis
+        r[1] *= -1.0
+        for i, v in enumerate(r.reshape(-1)):
+            p2.model.r[i] = float(v)
+        want2 = port.detect(raw2, p2)
+        got2 = ctx.detect(raw2, common.to_vp(p2), pinned=True)
+        np.testing.assert_array_equal(got2["flat"], want2["flat"])
+        check_frame(got2, 0, want2)
+    finally:
+        ctx.set_strips(2)
+
+
+@pytest.mark.parametrize("strips", [1, 3, 6])
+def test_lone_frames_replayed_as_a_graph_from_a_pinned_ring(ctx, port, strips):
+    """A camera's ring of pinned buffers: the first call launches directly, the second is captured into a CUDA graph,
+    the following ones replay it with the upload nodes repointed.  Distinct frames (one of them leaving the exactness
+    bound, which the host has to redo after a replay) must each give their own oracle result."""
+    p, f0, _ = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7)
+    h, w = 2 * p.hq, 2 * p.wq
+    yy, xx = np.mgrid[0:h, 0:w]
+    stripes = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
+    frames = [f0, common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=2, n_balls=5, seed=8)[1],
+              common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, frame="noise", seed=9)[1], stripes]
+    wants = [port.detect(f, p) for f in frames]
+    assert wants[3]["max_abs_sat"] > 2 ** 24
+    vp = common.to_vp(p)
+    rb = vp.raw_frame_bytes()
+    ring = lib.PinnedArray((len(frames), rb), np.uint8)
+    pm = lib.PinnedArray((p.max_blobs,), lib.MATCH_DTYPE)
+    pc = lib.PinnedArray((1, 3), np.int32)
+    ctx.set_strips(strips)
+    launches = []
+    try:
+        for it in range(3):
+            for i, f in enumerate(frames):
+                ring.array[i] = f
+                pm.array[:] = np.zeros((), lib.MATCH_DTYPE)
+                n0 = ctx.launch_count()
+                ctx.detect_host_into(ring.ptr.value + i * rb, 1, vp, pm.ptr.value, pc.ptr.value)
+                launches.append(ctx.launch_count() - n0)
+                np.testing.assert_array_equal(pc.array[0], wants[i]["counter"])
+                common.assert_matches_equal(pm.array[: min(int(pc.array[0, 0]), p.max_blobs)].copy(), wants[i]["matches"])
+                assert ctx.sat_fallbacks() == (1 if i == 3 else 0)
+        # the replays count the kernels they launch like direct calls do (flagged frame: + the redo)
+        assert launches[8] == launches[4] == launches[5] and launches[11] == launches[7] > launches[4]
+        # same thing with the graph switched off
+        ctx.set_latency_graph(False)
+        n0 = ctx.launch_count()
+        ctx.detect_host_into(ring.ptr.value, 1, vp, pm.ptr.value, pc.ptr.value)
+        assert ctx.launch_count() - n0 == launches[4]
+        np.testing.assert_array_equal(pc.array[0], wants[0]["counter"])
+        common.assert_matches_equal(pm.array[: int(pc.array[0, 0])].copy(), wants[0]["matches"])
+    finally:
+        ctx.set_latency_graph(True)
+        ctx.set_strips(2)
+        ring.free(); pm.free(); pc.free()
+
+
 def test_detect_blob_overflow_keeps_first_in_raster_order(ctx, port):
     p, raw, _ = common.make_case(wq=160, hq=120, frame="noise", seed=9, max_blobs=50)
     want = port.detect(raw, p)

@@ -1196,6 +1196,70 @@ __device__ __forceinline__ int grad_dot_opaque(uint32_t R, uint32_t L, uint32_t 
 	return (int)pos - (int)neg;
 }
 
+/* (the two helpers below restate the body of row_gradscan for k_grad_rowscan_wide; row_gradscan keeps its own copy because
+ * ptxas allocates 8 registers more for it when it is written in terms of them, which costs the batch path occupancy) */
+/* gradDot of the four pixels x0..x0+3 of row y (gradientDot.cl:22-30; pixels beyond the row end give 0); `vec`: rows are
+ * 16-byte aligned, `pairs`: the R/L taps of the four pixels are two aligned 8-byte pairs each */
+__device__ __forceinline__ void grad_dot4(const uint32_t* __restrict__ row, const uint32_t* __restrict__ up, const uint32_t* __restrict__ dn, int x0, int wf,
+                                          int o, bool vec, bool pairs, int (&g)[4])
+{
+	uint32_t U[4], D[4], Rr[4], Ll[4];
+	if (vec) {
+		const uint4 u4 = __ldg(reinterpret_cast<const uint4*>(up + x0));
+		const uint4 d4 = __ldg(reinterpret_cast<const uint4*>(dn + x0));
+		U[0] = u4.x; U[1] = u4.y; U[2] = u4.z; U[3] = u4.w;
+		D[0] = d4.x; D[1] = d4.y; D[2] = d4.z; D[3] = d4.w;
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int x = min(x0 + k, wf - 1);
+			U[k] = __ldg(up + x);
+			D[k] = __ldg(dn + x);
+		}
+	}
+	if (pairs && x0 - o >= 0 && x0 + 3 + o <= wf - 1) { /* no tap of these 4 pixels clamps */
+		const uint2 r0 = __ldg(reinterpret_cast<const uint2*>(row + x0 + o)), r1 = __ldg(reinterpret_cast<const uint2*>(row + x0 + o + 2));
+		const uint2 l0 = __ldg(reinterpret_cast<const uint2*>(row + x0 - o)), l1 = __ldg(reinterpret_cast<const uint2*>(row + x0 - o + 2));
+		Rr[0] = r0.x; Rr[1] = r0.y; Rr[2] = r1.x; Rr[3] = r1.y;
+		Ll[0] = l0.x; Ll[1] = l0.y; Ll[2] = l1.x; Ll[3] = l1.y;
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			const int x = x0 + k;
+			Rr[k] = __ldg(row + min(x + o, wf - 1));
+			Ll[k] = __ldg(row + clampi(x - o, 0, wf - 1));
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		g[k] = x0 + k < wf ? grad_dot_opaque(Rr[k], Ll[k], U[k], D[k]) : 0;
+}
+
+/* gradDot and row prefix sums of four pixels to memory; returns true if a prefix left the exactness bound */
+template <class SumT>
+__device__ __forceinline__ bool store_grad4(float* __restrict__ grow, SumT* __restrict__ srow, int x0, int wf, bool vec, const int (&g)[4], int base)
+{
+	const int p1 = g[0] + g[1], p2 = p1 + g[2], p3 = p2 + g[3];
+	const int s0 = base + g[0], s1 = base + p1, s2 = base + p2, s3 = base + p3;
+	const bool bad = max(max(abs(s0), abs(s1)), max(abs(s2), abs(s3))) >= SAT_EXACT_LIMIT;
+	if (vec) {
+		*reinterpret_cast<float4*>(grow + x0) = make_float4(small_int_to_float(g[0]), small_int_to_float(g[1]), small_int_to_float(g[2]), small_int_to_float(g[3]));
+		if constexpr (std::is_integral<SumT>::value)
+			*reinterpret_cast<int4*>(srow + x0) = make_int4(s0, s1, s2, s3);
+		else /* fp32: exact below 2^22; anything at or above SAT_EXACT_LIMIT raises the flag and is never used */
+			*reinterpret_cast<float4*>(srow + x0) = make_float4(small_int_to_float(s0), small_int_to_float(s1), small_int_to_float(s2), small_int_to_float(s3));
+	} else {
+		const int s[4] = { s0, s1, s2, s3 };
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (x0 + k < wf) {
+				grow[x0 + k] = (float)g[k];
+				srow[x0 + k] = (SumT)s[k];
+			}
+	}
+	return bad;
+}
+
 template <class SumT>
 __device__ __forceinline__ bool row_gradscan(const uint32_t* __restrict__ img, int y, int wf, int hf, int o, int lane, float* __restrict__ grow,
                                              SumT* __restrict__ srow)
@@ -1286,6 +1350,49 @@ __global__ void __launch_bounds__(ROWSCAN_WARPS * 32) k_grad_rowscan(const uint3
 		return;
 	const size_t fbase = (size_t)blockIdx.y * wf * hf;
 	if (row_gradscan(flat + fbase, y, wf, hf, o, lane, grad + fbase + y * wf, rowsum + fbase + y * wf))
+		flag[blockIdx.y] = 1;
+}
+
+/* K2a for a LONE frame (latency path): one CTA per row, warp w takes pixels [128w, 128w+128) -- every load of the row is
+ * in flight at once and the row sum is a two-level scan (lanes, then warps through shared memory) instead of a carry
+ * handed from segment to segment.  A single frame offers k_grad_rowscan one warp per row = ~7 warps per SM, each
+ * walking its row in ~10 dependent steps; here the same work is one memory round trip deep.  Integer sums: the result
+ * does not depend on the order, bit-identical to k_grad_rowscan. */
+constexpr int ROWWIDE_MAX_WARPS = 32;
+template <class SumT>
+__global__ void __launch_bounds__(ROWWIDE_MAX_WARPS * 32) k_grad_rowscan_wide(const uint32_t* __restrict__ flat, float* __restrict__ grad,
+                                                                             SumT* __restrict__ rowsum, int wf, int hf, int o, int* __restrict__ flag)
+{
+	__shared__ int totals[ROWWIDE_MAX_WARPS];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+	const int y = blockIdx.x;
+	const size_t fbase = (size_t)blockIdx.y * wf * hf;
+	const uint32_t* img = flat + fbase;
+	const bool vec = (wf & 3) == 0;
+	const bool pairs = vec && (o & 1) == 0;
+	const int x0 = warp * 128 + lane * 4;
+	int g[4] = { 0, 0, 0, 0 };
+	if (x0 < wf)
+		grad_dot4(img + y * wf, img + min(y + o, hf - 1) * wf, img + max(y - o, 0) * wf, x0, wf, o, vec, pairs, g);
+	const int p3 = ((g[0] + g[1]) + g[2]) + g[3];
+	int incl = p3;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int t = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d)
+			incl += t;
+	}
+	if (lane == 31)
+		totals[warp] = incl;
+	__syncthreads();
+	int before = lane < warp && lane < n_warps ? totals[lane] : 0; /* warps to the left of this one */
+#pragma unroll
+	for (int d = 16; d; d >>= 1)
+		before += __shfl_xor_sync(0xffffffffu, before, d);
+	bool bad = false;
+	if (x0 < wf)
+		bad = store_grad4(grad + fbase + y * wf, rowsum + fbase + y * wf, x0, wf, vec, g, before + incl - p3);
+	if (bad)
 		flag[blockIdx.y] = 1;
 }
 
@@ -2283,14 +2390,46 @@ __device__ __forceinline__ void emit_match(const uint32_t* __restrict__ im, cons
 	store_match(dst, mx, my, color, centre, c, score);
 }
 
-/* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp */
+/* The exactness bound of the summed-area table of one frame from the per-segment column sums of k_circ_stream_rs:
+ * |SAT(x, y)| <= |sum of the segments above| + max |running sum inside the segment| (conservative).  Columns x_begin,
+ * x_begin + x_step, ... < w per thread; called by a whole CTA, true when one of its columns may have left the bound. */
+__device__ __forceinline__ bool sat_bound_exceeded(const float* __restrict__ segsum, const float* __restrict__ segmax, int n_seg, int w, int f, int x_begin,
+                                                   int x_step)
+{
+	bool bad = false;
+	for (int x = x_begin; x < w; x += x_step) {
+		const float* ss = segsum + (size_t)f * n_seg * w + x;
+		const float* sm = segmax + (size_t)f * n_seg * w + x;
+		float carry = 0.f;
+#pragma unroll 8
+		for (int k = 0; k < n_seg; k++) { /* the loads do not depend on the carry: eight segments in flight */
+			bad |= !(__fadd_rn(fabsf(carry), sm[k * w]) < (float)SAT_EXACT_LIMIT);
+			carry = __fadd_rn(carry, ss[k * w]);
+		}
+	}
+	return __syncthreads_or(bad);
+}
+
+/* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp.
+ * Latency path (segsum != nullptr): the grid has ceil(w/256) more CTAs per frame, which evaluate the exactness bound of
+ * the SAT next to the record warps and raise the frame's flag for the HOST to see -- the caller then redoes the frame in
+ * sequential order (k_sat_check_fix + k_circ_stream + this kernel again) instead of launching that pair of kernels for
+ * every frame just to have them exit. */
 __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h, int radius,
                                                     int max_matches, const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
-                                                    const uint32_t* __restrict__ masks, int wpr, uint8_t* __restrict__ matches, size_t match_frame_stride)
+                                                    const uint32_t* __restrict__ masks, int wpr, uint8_t* __restrict__ matches, size_t match_frame_stride,
+                                                    const float* __restrict__ segsum = nullptr, const float* __restrict__ segmax = nullptr, int n_seg = 0,
+                                                    int* __restrict__ flag = nullptr)
 {
 	const int lane = threadIdx.x & 31;
-	const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
 	const int f = blockIdx.y;
+	const int n_row_ctas = (h + 7) >> 3;
+	if (blockIdx.x >= n_row_ctas) { /* only launched when segsum is given: one thread per column */
+		if (flag[f] == 0 && sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w) && threadIdx.x == 0)
+			flag[f] = 2;
+		return;
+	}
+	const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
 	if (y >= h)
 		return;
 	const int32_t* rc = rowcount + (size_t)f * h;

@@ -28,6 +28,7 @@ struct LutEntry {
 	float2* d = nullptr;
 	TileEntry* tiles = nullptr; /* footprint of every 64x16 flat tile (k_tile_table) */
 	uint64_t stamp = 0;
+	std::vector<int> rows_needed; /* per tile row: raw Bayer rows [0, n) its tiles read (host copy, made on first use by the latency path) */
 };
 
 struct ProfEntry {
@@ -36,15 +37,64 @@ struct ProfEntry {
 };
 
 constexpr int HOST_SLOTS = 3;
+constexpr int MAX_STRIPS = 16;
+
+/* Latency path: the raw frame is uploaded in n chunks of rows and the row-local stages of the pipeline (reprojection,
+ * gradient + row sums, circularity segments) follow strip by strip, so that only the last strip's work, the exactness
+ * check and the record kernel remain once the upload has ended.  ty_end[k] = tile rows of the flat image whose raw rows
+ * are on the device after chunk k; uploaded[k] is recorded on the copy stream behind chunk k. */
+struct StripPlan {
+	int n = 0;
+	int raw_end[MAX_STRIPS]; /* chunk k = raw rows [raw_end[k-1], raw_end[k]) */
+	int ty_end[MAX_STRIPS];
+	cudaEvent_t uploaded[MAX_STRIPS];
+};
 
 struct HostSlot {
 	uint8_t* raw = nullptr;
 	uint8_t* flat = nullptr;
 	float* grad = nullptr;
 	float* circ = nullptr;
-	vp_match* matches = nullptr;
-	int32_t* counter = nullptr;
+	/* one allocation, one download: [counter 3 x frames][flags frames][pad to 16][matches frames x max_blobs x 22 B] */
+	uint8_t* results = nullptr;
+	uint8_t* results_host = nullptr; /* pinned mirror (latency path) */
+	size_t off_matches = 0;
+	int32_t* counter = nullptr; /* = results */
+	int* flags = nullptr;       /* = results + 12 * frames */
+	vp_match* matches = nullptr; /* = results + off_matches */
 	cudaEvent_t uploaded = nullptr, computed = nullptr, downloaded = nullptr;
+};
+
+/* Everything the enqueued work of a lone frame depends on besides the frame's address: when two consecutive calls agree
+ * on all of it, the second one is captured into a CUDA graph and later calls replay it (one cudaGraphLaunch instead of
+ * ~6 driver calls per strip: the CPU, not the GPU, is what limits a finely chunked frame otherwise). */
+struct LoneFingerprint {
+	vp_params params;
+	const void* ptr[18];
+	int knob[10];
+};
+
+struct LoneFrameGraph {
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	LoneFingerprint fp;       /* of the last direct call (have_fp) or of the captured graph (exec) */
+	bool have_fp = false;
+	const uint8_t* h_raw = nullptr; /* frame address the upload nodes currently point at */
+	struct Upload { cudaGraphNode_t node; size_t off, bytes; };
+	std::vector<Upload> uploads;
+	std::vector<const void*> pinned; /* frame addresses already checked to be pinned host memory */
+	bool deferred = false;
+	uint64_t launches = 0;    /* kernels one replay launches */
+	uint64_t replays = 0;
+	void reset()
+	{
+		if (exec) cudaGraphExecDestroy(exec);
+		if (graph) cudaGraphDestroy(graph);
+		exec = nullptr;
+		graph = nullptr;
+		uploads.clear();
+		h_raw = nullptr;
+	}
 };
 
 } // namespace
@@ -96,6 +146,13 @@ struct vp_ctx {
 	size_t sync_cap = 0;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
+
+	cudaEvent_t strip_uploaded[MAX_STRIPS] = {};
+	cudaEvent_t strip_flat[1] = {}; /* all strips reprojected */
+	int strips = 2; /* chunks a lone frame's upload is cut into (vp_detect_host); 1 = upload, then compute */
+	cudaEvent_t lone_fork = nullptr;
+	bool latency_graph = true; /* replay the lone-frame sequence (chunked upload, strip kernels, download) as one CUDA graph */
+	LoneFrameGraph lone;
 
 	HostSlot slots[HOST_SLOTS];
 	size_t slot_frames = 0, slot_raw = 0, slot_nf = 0, slot_blobs = 0;
@@ -252,6 +309,7 @@ int get_lut(vp_ctx* ctx, const vp_camera_model* m, float height, float scale, fl
 	}
 	memcpy(slot->key, key, sizeof key);
 	slot->stamp = ++ctx->lut_clock;
+	slot->rows_needed.clear();
 	{
 		Stage st(ctx, "coord_table", 2);
 		dim3 b(32, 8), g(cdiv(wf, 32), cdiv(hf, 8));
@@ -379,10 +437,12 @@ int validate_params(vp_ctx* ctx, const vp_params* p)
 size_t raw_frame_bytes(const vp_params* p) { return (size_t)p->wq * p->hq * (size_t)vp_format_pixel_size(p->fmt); }
 
 int launch_peaks_emit(vp_ctx* ctx, cudaStream_t stream, const uint32_t* flat, const float* circ, int w, int h, int n, int radius, int max_matches,
-                      const int32_t* first_slot, const int32_t* rowcount, const uint32_t* masks, uint8_t* matches, size_t match_stride)
+                      const int32_t* first_slot, const int32_t* rowcount, const uint32_t* masks, uint8_t* matches, size_t match_stride,
+                      const float* segsum = nullptr, const float* segmax = nullptr, int n_seg = 0, int* flag = nullptr)
 {
-	k_peaks_emit<<<dim3(cdiv(h, 8), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks, cdiv(w, 32), matches,
-	                                                           match_stride);
+	/* segsum given: ceil(w/256) more CTAs per frame check the exactness bound of the SAT (see k_peaks_emit) */
+	k_peaks_emit<<<dim3(cdiv(h, 8) + (segsum ? cdiv(w, 256) : 0), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks, cdiv(w, 32),
+	                                                                          matches, match_stride, segsum, segmax, n_seg, flag);
 	return check_launch(ctx, "k_peaks_emit");
 }
 
@@ -451,17 +511,7 @@ __global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict_
 	const int f = blockIdx.x;
 	int state = flag[f];
 	if (state == 0) {
-		bool bad = false;
-		for (int x = threadIdx.x; x < w; x += 1024) {
-			const float* ss = segsum + (size_t)f * n_seg * w + x;
-			const float* sm = segmax + (size_t)f * n_seg * w + x;
-			float carry = 0.f;
-			for (int k = 0; k < n_seg; k++) {
-				bad |= !(__fadd_rn(fabsf(carry), sm[k * w]) < (float)SAT_EXACT_LIMIT);
-				carry = __fadd_rn(carry, ss[k * w]);
-			}
-		}
-		if (!__syncthreads_or(bad))
+		if (!sat_bound_exceeded(segsum, segmax, n_seg, w, f, threadIdx.x, 1024))
 			return;
 		if (threadIdx.x == 0)
 			flag[f] = 2;
@@ -473,6 +523,14 @@ __global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict_
 	if (threadIdx.x < 3)
 		counter[3 * f + threadIdx.x] = 0;
 	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
+}
+
+/* rows per CTA of the streaming circularity kernels: 128 for batches (few halo rows per segment); a lone frame has only
+ * hf/128 x 14 CTAs to offer, so shorter segments trade halo work for shorter dependent chains and a full GPU */
+int circ_seg_rows(int n_frames)
+{
+	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
+	return seg_env > 0 ? seg_env : (n_frames >= 3 ? 128 : 32);
 }
 
 int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
@@ -554,6 +612,7 @@ int vp_ctx_create(int device, vp_ctx** out)
 	c->device = device;
 	c->sm_count = prop.multiProcessorCount;
 	if (getenv("VP_HOIST_CHUNK")) c->hoist_chunk = atoi(getenv("VP_HOIST_CHUNK")); /* tuning aid */
+	if (getenv("VP_STRIPS")) c->strips = std::max(1, std::min(MAX_STRIPS, atoi(getenv("VP_STRIPS")))); /* tuning aid */
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking) != cudaSuccess
 	    || cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking) != cudaSuccess) {
 		delete c;
@@ -566,6 +625,10 @@ int vp_ctx_create(int device, vp_ctx** out)
 			ok = ok && cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess;
 		ok = ok && cudaEventCreateWithFlags(&c->lane_done[l], cudaEventDisableTiming) == cudaSuccess;
 	}
+	for (int k = 0; k < MAX_STRIPS && ok; k++)
+		ok = ok && cudaEventCreateWithFlags(&c->strip_uploaded[k], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->strip_flat[0], cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&c->lone_fork, cudaEventDisableTiming) == cudaSuccess;
 	if (!ok) {
 		vp_ctx_destroy(c);
 		return fail(nullptr, VP_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -577,7 +640,8 @@ int vp_ctx_create(int device, vp_ctx** out)
 static void free_slots(vp_ctx* c)
 {
 	for (HostSlot& s : c->slots) {
-		cudaFree(s.raw); cudaFree(s.flat); cudaFree(s.grad); cudaFree(s.circ); cudaFree(s.matches); cudaFree(s.counter);
+		cudaFree(s.raw); cudaFree(s.flat); cudaFree(s.grad); cudaFree(s.circ); cudaFree(s.results);
+		if (s.results_host) cudaFreeHost(s.results_host);
 		if (s.uploaded) cudaEventDestroy(s.uploaded);
 		if (s.computed) cudaEventDestroy(s.computed);
 		if (s.downloaded) cudaEventDestroy(s.downloaded);
@@ -612,11 +676,16 @@ void vp_ctx_destroy(vp_ctx* c)
 		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
 	}
 	if (c->fork) cudaEventDestroy(c->fork);
+	for (int k = 0; k < MAX_STRIPS; k++)
+		if (c->strip_uploaded[k]) cudaEventDestroy(c->strip_uploaded[k]);
+	if (c->strip_flat[0]) cudaEventDestroy(c->strip_flat[0]);
+	if (c->lone_fork) cudaEventDestroy(c->lone_fork);
 	for (int l = 0; l < vp_ctx::MAX_LANES; l++)
 		cudaFree(c->agg[l]);
 	cudaFree(c->sync_words);
 	cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
 	if (c->flag_host) cudaFreeHost(c->flag_host);
+	c->lone.reset();
 	free_slots(c);
 	cudaStreamDestroy(c->stream);
 	cudaStreamDestroy(c->copy_in);
@@ -677,6 +746,23 @@ int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames) /* frames one CTA of the hoi
 	ctx->hoist_chunk = frames;
 	return VP_OK;
 }
+
+int vp_ctx_set_strips(vp_ctx* ctx, int strips) /* chunks the upload of a lone frame is cut into (latency path of vp_detect_host) */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	REQUIRE(ctx, strips >= 1 && strips <= MAX_STRIPS, "strips must be in [1, %d]", MAX_STRIPS);
+	ctx->strips = strips;
+	return VP_OK;
+}
+
+int vp_ctx_set_latency_graph(vp_ctx* ctx, int on) /* A/B switch: replay the lone-frame sequence of vp_detect_host as a CUDA graph (default on) */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->latency_graph = on != 0;
+	return VP_OK;
+}
+
+uint64_t vp_latency_graph_replays(const vp_ctx* ctx) { return ctx ? ctx->lone.replays : 0; }
 
 int vp_ctx_set_lanes(vp_ctx* ctx, int lanes) /* concurrent streams the groups of one batch are spread over */
 {
@@ -1182,9 +1268,26 @@ int vp_blob_score(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp_img* o
 }
 
 /* ---- fused detection -------------------------------------------------------------------------- */
+/* how vp_detect_host drives the fused path for a few frames (latency path) */
+struct DetectOpts {
+	const StripPlan* plan = nullptr; /* one frame, still arriving chunk by chunk on the copy stream */
+	int* flags = nullptr;            /* exactness flags live here (next to the results the host downloads) instead of ctx->flag */
+	bool defer_fallback = false;     /* the SAT bound is checked inside the record kernel and the HOST redoes flagged frames (redo_flagged) */
+	mutable bool deferred = false;   /* out: the call really left the fallback to the host (one group, SAT-free flow) */
+};
+static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* p, uint8_t* d_flat, float* d_grad, float* d_circ,
+                             vp_match* d_matches, int32_t* d_counter, const DetectOpts& opts);
+
 int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* p, uint8_t* d_flat, float* d_grad, float* d_circ,
                            vp_match* d_matches, int32_t* d_counter)
 {
+	return detect_batch_impl(ctx, d_raw, n_frames, p, d_flat, d_grad, d_circ, d_matches, d_counter, DetectOpts());
+}
+
+static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* p, uint8_t* d_flat, float* d_grad, float* d_circ,
+                             vp_match* d_matches, int32_t* d_counter, const DetectOpts& opts)
+{
+	const StripPlan* const plan = opts.plan;
 	REQUIRE(ctx, ctx, "ctx is null");
 	int rc = validate_params(ctx, p);
 	if (rc) return rc;
@@ -1203,10 +1306,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
-	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
-	/* rows per CTA of the streaming circularity kernels: 128 for batches (few halo rows per segment); a lone frame has only
-	 * hf/128 x 14 CTAs to offer, so shorter segments trade halo work for shorter dependent chains and a full GPU */
-	const int seg = seg_env > 0 ? seg_env : (n_frames >= 3 ? 128 : 32);
+	const int seg = circ_seg_rows(n_frames);
 	const int n_seg = cdiv(hf, seg);
 	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
 	if (sat_free) {
@@ -1266,13 +1366,17 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 	const bool staged = ctx->staged_reproject != 0 && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
 	const bool hoisted = staged && ctx->staged_reproject == 2;
 	const int ns = need_score(p->circ_threshold, p->min_score);
+	const bool by_strips = plan && plan->n > 1 && n_frames == 1 && hoisted && sat_free && !ctx->profiling;
+	int* const flags = opts.flags ? opts.flags : ctx->flag;
+	const bool defer_fallback = opts.defer_fallback && sat_free && n_groups == 1; /* only the SAT-free flow has a check to move */
+	opts.deferred = defer_fallback;
 
 	{
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
 		/* enough CTAs to clear the blob masks of a lone frame in one pass (the kernel strides over them) */
 		const int prep_ctas = std::max(cdiv(n, 256), std::min(cdiv(n * wpr, 256), 4 * ctx->sm_count));
-		k_peaks_prepare<<<prep_ctas, 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, ctx->flag, ctx->masks, n * wpr,
+		k_peaks_prepare<<<prep_ctas, 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, flags, ctx->masks, n * wpr,
 		                                                       fused_sat ? ctx->sync_words : nullptr, fused_sat ? n_frames * (1 + n_strips) : 0);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
@@ -1280,6 +1384,49 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		CK(ctx, cudaEventRecord(ctx->fork, ctx->stream));
 		for (int l = 1; l < lanes; l++)
 			CK(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->fork, 0));
+	}
+	if (plan && !by_strips) /* configuration without a strip form: wait for the whole frame */
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, plan->uploaded[plan->n - 1], 0));
+	if (by_strips) {
+		/* One frame whose raw rows are still arriving: after chunk k the tile rows < ty_end[k] can be reprojected, on a
+		 * stream of their own, so that only the last strip's reprojection is left when the upload ends.  Same kernel,
+		 * restricted to tile rows by offsetting its tables and images: every tile is computed exactly once from the same
+		 * inputs.  Only the reprojection is cut up: it is the one stage of a lone frame that spans several waves of CTAs
+		 * and therefore gets shorter with fewer rows.  The gradient/row-sum and circularity kernels of a single frame are
+		 * single-wave and latency-bound -- a strip of them takes as long as the whole frame (measured: pipelining all three
+		 * stages strip by strip made the frame slower, profiles/r01_latency.txt). */
+		cudaStream_t sA = ctx->lane_stream[1];
+		CK(ctx, cudaEventRecord(ctx->fork, ctx->stream)); /* orders the side stream behind earlier work (and is the fork point of a capture) */
+		CK(ctx, cudaStreamWaitEvent(sA, ctx->fork, 0));
+		const int tiles_x = cdiv(wf, FT_W), tiles_y = cdiv(hf, FT_H);
+		uint32_t* flat = (uint32_t*)d_flat;
+		if (!ctx->hoist_attr) {
+			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+			ctx->hoist_attr = true;
+		}
+		int ty_done = 0;
+		for (int k = 0; k < plan->n; k++) {
+			CK(ctx, cudaStreamWaitEvent(sA, plan->uploaded[k], 0));
+			const int ty_end = k == plan->n - 1 ? tiles_y : std::min(plan->ty_end[k], tiles_y);
+			if (ty_end <= ty_done)
+				continue;
+			Stage st(ctx, "reproject", 1, sA);
+			const size_t row0 = (size_t)ty_done * FT_H;
+			const dim3 grid(tiles_x, ty_end - ty_done, 1);
+			if (p->fmt == VP_FMT_RGGB8)
+				k_reproject_hoist<FMT_RGGB, 4><<<grid, 256, HOIST_SMEM, sA>>>(d_raw, raw_bytes, lut + row0 * wf, tiles + (size_t)ty_done * tiles_x, flat + row0 * wf,
+				                                                                p->wq, p->hq, wf, hf - (int)row0, 1, 1, ctx->one);
+			else
+				k_reproject_hoist<FMT_GRBG, 4><<<grid, 256, HOIST_SMEM, sA>>>(d_raw, raw_bytes, lut + row0 * wf, tiles + (size_t)ty_done * tiles_x, flat + row0 * wf,
+				                                                                p->wq, p->hq, wf, hf - (int)row0, 1, 1, ctx->one);
+			if ((rc = check_launch(ctx, "k_reproject_hoist (strip)"))) return rc;
+			ty_done = ty_end;
+		}
+		CK(ctx, cudaEventRecord(ctx->strip_flat[0], sA));
+		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->strip_flat[0], 0)); /* join: the flat image is complete */
 	}
 	for (int gi = 0; gi < n_groups; gi++) {
 		const int f0 = gi * G;
@@ -1292,11 +1439,11 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		float* grad = d_grad + (size_t)f0 * nf;
 		float* circ = d_circ + (size_t)f0 * nf;
 		const uint8_t* raw = d_raw + (size_t)f0 * raw_bytes;
-		int* flag = ctx->flag + f0;
+		int* flag = flags + f0;
 		int32_t* counter = d_counter + 3 * (size_t)f0;
 		int32_t* rowcount = ctx->rowcount + (size_t)f0 * hf;
 		uint32_t* masks = ctx->masks + (size_t)f0 * hf * wpr;
-		{
+		if (!by_strips) {
 			Stage st(ctx, "reproject", 1, s);
 			if (hoisted) {
 				/* one CTA keeps a tile's weights in registers for `chunk` frames; enough CTAs to fill the GPU several times */
@@ -1353,7 +1500,12 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		}
 		if (sat_free) {
 			Stage st(ctx, "grad_rowscan", 1, s);
-			k_grad_rowscan<float><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
+			static const int wide_env = getenv("VP_GRAD_WIDE") ? atoi(getenv("VP_GRAD_WIDE")) : -1; /* tuning aid / A-B */
+			const bool wide = (wide_env >= 0 ? wide_env != 0 : g <= 2) && cdiv(wf, 128) <= ROWWIDE_MAX_WARPS;
+			if (wide) /* one or two frames: a CTA per row, the whole row in flight at once */
+				k_grad_rowscan_wide<float><<<dim3(hf, g), cdiv(wf, 128) * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
+			else
+				k_grad_rowscan<float><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
 			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
 		} else if (fused_sat) {
 			Stage st(ctx, "grad_sat", 1, s);
@@ -1397,7 +1549,7 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 #undef VP_CSR
 				if ((rc = check_launch(ctx, "k_circ_stream_rs"))) return rc;
 			}
-			{
+			if (!defer_fallback) {
 				/* the exactness bound of the summed-area table, checked after the fact; frames that left it (or whose row sums
 				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
 				Stage st(ctx, "sat_check", 2, s);
@@ -1458,8 +1610,13 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		}
 		{
 			Stage st(ctx, "peaks_emit", 1, s);
-			rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
-			                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22);
+			if (defer_fallback)
+				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
+				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22, ctx->segsum[lane], ctx->segmax[lane], n_seg,
+				                       flag);
+			else
+				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
+				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22);
 			if (rc) return rc;
 		}
 	}
@@ -1467,9 +1624,43 @@ int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, cons
 		CK(ctx, cudaEventRecord(ctx->lane_done[l], ctx->lane_stream[l]));
 		CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_done[l], 0));
 	}
-	CK(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	ctx->last_fallbacks = -n_frames; /* negative: flag_host holds n flags not summed yet */
+	if (!opts.flags) {
+		CK(ctx, cudaMemcpyAsync(ctx->flag_host, ctx->flag, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		ctx->last_fallbacks = -n_frames; /* negative: flag_host holds n flags not summed yet */
+	}
 	return VP_OK;
+}
+
+/* Second half of a deferred fallback (latency path): the host has seen a raised flag among `n_frames` frames.  Those
+ * frames are redone in the reference's sequential order -- forget what the fast pass published, rebuild the SAT, literal
+ * circularity -- and the records of all frames are written again (idempotent for the clean ones). */
+static int redo_flagged(vp_ctx* ctx, int n_frames, const vp_params* p, uint8_t* d_flat, float* d_grad, float* d_circ, vp_match* d_matches,
+                        int32_t* d_counter, int* flags)
+{
+	const int wf = p->wf, hf = p->hf, wpr = cdiv(wf, 32);
+	const int seg = circ_seg_rows(n_frames), n_seg = cdiv(hf, seg), r = p->circle_radius;
+	const int ns = need_score(p->circ_threshold, p->min_score);
+	cudaStream_t s = ctx->stream;
+	uint32_t* flat = (uint32_t*)d_flat;
+	float* sat = ctx->sat[0];
+	int rc;
+	Stage st(ctx, "sat_check", 3, s);
+	k_sat_check_fix<<<n_frames, 1024, 0, s>>>(ctx->segsum[0], ctx->segmax[0], n_seg, d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount,
+	                                          ctx->masks, wpr);
+#define VP_CSF(RR)                                                                                                             \
+	case RR: {                                                                                                                 \
+		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, n_frames);                                                              \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
+		                                       ctx->rowcount, ctx->masks, wpr, 1);                                             \
+	} break;
+	switch (r) {
+		VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
+	}
+#undef VP_CSF
+	if ((rc = check_launch(ctx, "sat_check/fallback (redo)"))) return rc;
+	return launch_peaks_emit(ctx, s, flat, d_circ, wf, hf, n_frames, p->blob_radius, p->max_blobs, ctx->first_slot, ctx->rowcount, ctx->masks,
+	                         (uint8_t*)d_matches, (size_t)p->max_blobs * 22);
 }
 
 int vp_blobs_to_field_device(vp_ctx* ctx, const vp_match* d_matches, const int32_t* d_counter, int n_frames, int max_blobs, float field_scale, float off_x,
@@ -1501,6 +1692,63 @@ int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n)
 	return VP_OK;
 }
 
+/* Upload schedule of a lone frame for this geometry: tile rows are handed out in `strips` equal shares, and chunk k ends
+ * at the last raw row the tiles of share k read (known per geometry from the tile table, copied to the host once).  A
+ * camera whose flat rows do not advance with the raw rows (rolled by 90 or 180 degrees) gets a plan whose first chunk is
+ * most of the frame: still correct, just without the overlap.  plan->n = 0 when there is nothing to gain. */
+static int make_strip_plan(vp_ctx* ctx, const vp_params* p, StripPlan* plan)
+{
+	plan->n = 0;
+	if (ctx->staged_reproject != 2 || p->sample_mode != VP_SAMPLE_BILINEAR_RTE || ctx->profiling)
+		return VP_OK;
+	const int wf = p->wf, hf = p->hf, H = 2 * p->hq;
+	const int tiles_x = cdiv(wf, FT_W), tiles_y = cdiv(hf, FT_H);
+	const float2* lut;
+	const TileEntry* tiles;
+	int rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, p->wq, p->hq, &lut, &tiles);
+	if (rc) return rc;
+	LutEntry* entry = nullptr;
+	for (LutEntry& e : ctx->luts)
+		if (e.tiles == tiles)
+			entry = &e;
+	if (!entry)
+		return VP_OK;
+	if (entry->rows_needed.empty()) {
+		std::vector<TileEntry> host((size_t)tiles_x * tiles_y);
+		CK(ctx, cudaMemcpyAsync(host.data(), tiles, host.size() * sizeof(TileEntry), cudaMemcpyDeviceToHost, ctx->stream));
+		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		entry->rows_needed.assign(tiles_y, 0);
+		for (int ty = 0; ty < tiles_y; ty++) {
+			int need = 0;
+			for (int tx = 0; tx < tiles_x; tx++) {
+				const TileEntry& e = host[(size_t)ty * tiles_x + tx];
+				int rows = H; /* direct gather: footprint not known */
+				if (e.flags & 1) {
+					const int last = std::min(p->hq - 1, std::max(0, e.jb + e.height - 1)); /* staged quad rows are clamped into the image */
+					rows = 2 * last + 2;
+				}
+				need = std::max(need, rows);
+			}
+			entry->rows_needed[ty] = need;
+		}
+	}
+	const int n = std::min(ctx->strips, tiles_y);
+	if (n < 2)
+		return VP_OK;
+	int ty0 = 0, need = 0;
+	for (int k = 0; k < n; k++) {
+		const int ty1 = k == n - 1 ? tiles_y : (int)((long long)tiles_y * (k + 1) / n);
+		for (int ty = ty0; ty < ty1; ty++)
+			need = std::max(need, entry->rows_needed[ty]);
+		plan->ty_end[k] = ty1;
+		plan->raw_end[k] = k == n - 1 ? H : std::min(need, H);
+		plan->uploaded[k] = ctx->strip_uploaded[k];
+		ty0 = ty1;
+	}
+	plan->n = n;
+	return VP_OK;
+}
+
 static int ensure_slots(vp_ctx* ctx, size_t frames, size_t raw_bytes, size_t nf, size_t blobs)
 {
 	if (frames <= ctx->slot_frames && raw_bytes <= ctx->slot_raw && nf <= ctx->slot_nf && blobs <= ctx->slot_blobs)
@@ -1514,8 +1762,13 @@ static int ensure_slots(vp_ctx* ctx, size_t frames, size_t raw_bytes, size_t nf,
 		CK(ctx, cudaMalloc(&s.flat, frames * nf * 4));
 		CK(ctx, cudaMalloc(&s.grad, frames * nf * 4));
 		CK(ctx, cudaMalloc(&s.circ, frames * nf * 4));
-		CK(ctx, cudaMalloc(&s.matches, frames * (blobs ? blobs : 1) * 22));
-		CK(ctx, cudaMalloc(&s.counter, frames * 12));
+		s.off_matches = (frames * 16 + 15) / 16 * 16;
+		const size_t res_bytes = s.off_matches + frames * (blobs ? blobs : 1) * 22;
+		CK(ctx, cudaMalloc(&s.results, res_bytes));
+		CK(ctx, cudaMallocHost(&s.results_host, res_bytes));
+		s.counter = (int32_t*)s.results;
+		s.flags = (int*)(s.results + frames * 12);
+		s.matches = (vp_match*)(s.results + s.off_matches);
 		CK(ctx, cudaEventCreateWithFlags(&s.uploaded, cudaEventDisableTiming));
 		CK(ctx, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
 		CK(ctx, cudaEventCreateWithFlags(&s.downloaded, cudaEventDisableTiming));
@@ -1524,6 +1777,159 @@ static int ensure_slots(vp_ctx* ctx, size_t frames, size_t raw_bytes, size_t nf,
 	ctx->slot_raw = raw_bytes;
 	ctx->slot_nf = nf;
 	ctx->slot_blobs = blobs;
+	return VP_OK;
+}
+
+/* upload (whole or in the plan's chunks on the copy stream), fused path, one download of results + counters + flags;
+ * nothing here blocks.  `forked`: the copy stream has to be ordered behind the compute stream first (stream capture). */
+static int enqueue_lone_frames(vp_ctx* ctx, HostSlot& s, const uint8_t* h_raw, int n_frames, const vp_params* p, const DetectOpts& opts, size_t raw_bytes,
+                               size_t res_bytes, bool forked)
+{
+	if (opts.plan) {
+		const StripPlan& plan = *opts.plan;
+		const size_t row_bytes = raw_bytes / (size_t)(2 * p->hq);
+		if (forked) {
+			CK(ctx, cudaEventRecord(ctx->lone_fork, ctx->stream));
+			CK(ctx, cudaStreamWaitEvent(ctx->copy_in, ctx->lone_fork, 0));
+		}
+		int done = 0;
+		for (int k = 0; k < plan.n; k++) {
+			const int end = plan.raw_end[k];
+			if (end > done)
+				CK(ctx, cudaMemcpyAsync(s.raw + (size_t)done * row_bytes, h_raw + (size_t)done * row_bytes, (size_t)(end - done) * row_bytes,
+				                        cudaMemcpyHostToDevice, ctx->copy_in));
+			CK(ctx, cudaEventRecord(plan.uploaded[k], ctx->copy_in));
+			done = std::max(done, end);
+		}
+	} else {
+		/* everything in order on one stream, no cross-stream hops */
+		CK(ctx, cudaMemcpyAsync(s.raw, h_raw, (size_t)n_frames * raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+	}
+	static const bool upload_only = getenv("VP_DEBUG_UPLOAD_ONLY") != nullptr; /* measurement aid: the copies alone (results are stale) */
+	if (upload_only) {
+		if (opts.plan)
+			CK(ctx, cudaStreamWaitEvent(ctx->stream, opts.plan->uploaded[opts.plan->n - 1], 0));
+	} else {
+		int rc = detect_batch_impl(ctx, s.raw, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter, opts);
+		if (rc) return rc;
+	}
+	CK(ctx, cudaMemcpyAsync(s.results_host, s.results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return VP_OK;
+}
+
+static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p, LoneFingerprint* fp)
+{
+	memset(fp, 0, sizeof *fp);
+	fp->params = *p;
+	const float2* lut = nullptr;
+	const TileEntry* tiles = nullptr;
+	for (LutEntry& e : ctx->luts) { /* the table this geometry would use, if it exists already (no side effects here) */
+		uint8_t key[104];
+		memset(key, 0, sizeof key);
+		memcpy(key, &p->model, 72);
+		memcpy(key + 72, &p->max_robot_height, 4);
+		memcpy(key + 76, &p->field_scale, 4);
+		memcpy(key + 80, &p->off_x, 4);
+		memcpy(key + 84, &p->off_y, 4);
+		memcpy(key + 88, &p->wf, 4);
+		memcpy(key + 92, &p->hf, 4);
+		memcpy(key + 96, &p->wq, 4);
+		memcpy(key + 100, &p->hq, 4);
+		if (memcmp(e.key, key, sizeof key) == 0) {
+			lut = e.d;
+			tiles = e.tiles;
+		}
+	}
+	const void* ptrs[18] = { s.raw, s.flat, s.grad, s.circ, s.results, s.results_host, ctx->rowsum[0], ctx->sat[0], ctx->segsum[0], ctx->segmax[0],
+		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->sync_words, ctx->agg[0] };
+	memcpy(fp->ptr, ptrs, sizeof ptrs);
+	const int knobs[10] = { ctx->staged_reproject, ctx->sat_free, ctx->stream_circ, ctx->fused_sat, ctx->hoist_chunk, ctx->group, ctx->lanes, ctx->strips,
+		                    ctx->profiling, 0 };
+	memcpy(fp->knob, knobs, sizeof knobs);
+}
+
+static bool is_pinned(LoneFrameGraph& lg, const void* host)
+{
+	for (const void* q : lg.pinned)
+		if (q == host)
+			return true;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	if (a.type != cudaMemoryTypeHost)
+		return false;
+	if (lg.pinned.size() >= 64)
+		lg.pinned.clear();
+	lg.pinned.push_back(host);
+	return true;
+}
+
+/* capture one lone-frame enqueue (copy stream forked from and joined back into the compute stream) and instantiate it;
+ * on any failure the capture is abandoned and the caller carries on with direct launches */
+static int capture_lone_frame(vp_ctx* ctx, HostSlot& s, const uint8_t* h_raw, const vp_params* p, const DetectOpts& opts, size_t raw_bytes, size_t res_bytes)
+{
+	LoneFrameGraph& lg = ctx->lone;
+	lg.reset();
+	const uint64_t launches0 = ctx->launches.load();
+	if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+		cudaGetLastError();
+		lg.have_fp = false;
+		return VP_OK;
+	}
+	const int rc = enqueue_lone_frames(ctx, s, h_raw, 1, p, opts, raw_bytes, res_bytes, true);
+	cudaGraph_t graph = nullptr;
+	const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+	const uint64_t launched = ctx->launches.load() - launches0;
+	ctx->launches -= launched; /* nothing ran */
+	LoneFingerprint after;
+	lone_fingerprint(ctx, s, p, &after);
+	if (rc != VP_OK || e != cudaSuccess || !graph || memcmp(&after, &lg.fp, sizeof after) != 0) {
+		cudaGetLastError();
+		if (graph) cudaGraphDestroy(graph);
+		lg.have_fp = false; /* do not try again until two direct calls agree once more */
+		return VP_OK;
+	}
+	cudaGraphExec_t exec = nullptr;
+	if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+		cudaGetLastError();
+		cudaGraphDestroy(graph);
+		lg.have_fp = false;
+		return VP_OK;
+	}
+	size_t n_nodes = 0;
+	cudaGraphGetNodes(graph, nullptr, &n_nodes);
+	std::vector<cudaGraphNode_t> nodes(n_nodes);
+	if (n_nodes)
+		cudaGraphGetNodes(graph, nodes.data(), &n_nodes);
+	for (cudaGraphNode_t nd : nodes) {
+		cudaGraphNodeType t;
+		if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeMemcpy)
+			continue;
+		cudaMemcpy3DParms mp;
+		if (cudaGraphMemcpyNodeGetParams(nd, &mp) != cudaSuccess)
+			continue;
+		const uint8_t* src = (const uint8_t*)mp.srcPtr.ptr;
+		if (src >= h_raw && src < h_raw + raw_bytes)
+			lg.uploads.push_back({ nd, (size_t)(src - h_raw), mp.extent.width });
+	}
+	cudaGetLastError();
+	size_t covered = 0;
+	for (const LoneFrameGraph::Upload& u : lg.uploads)
+		covered += u.bytes;
+	if (covered != raw_bytes) { /* the upload nodes were not all recognised: this graph could not be repointed at another frame */
+		cudaGraphExecDestroy(exec);
+		cudaGraphDestroy(graph);
+		lg.uploads.clear();
+		lg.have_fp = false;
+		return VP_OK;
+	}
+	lg.graph = graph;
+	lg.exec = exec;
+	lg.h_raw = h_raw;
+	lg.deferred = opts.deferred;
+	lg.launches = launched;
 	return VP_OK;
 }
 
@@ -1541,18 +1947,92 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 	rc = ensure_slots(ctx, (size_t)chunk, raw_bytes, nf, blobs);
 	if (rc) return rc;
 	if (n_frames <= chunk) {
-		/* latency path (a camera delivering one frame at a time): everything in order on one stream, no cross-stream hops */
+		/* latency path (a camera delivering one frame at a time) */
 		HostSlot& s = ctx->slots[0];
-		CK(ctx, cudaMemcpyAsync(s.raw, h_raw, (size_t)n_frames * raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		rc = vp_detect_batch_device(ctx, s.raw, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter);
-		if (rc) return rc;
-		if (blobs)
-			CK(ctx, cudaMemcpyAsync(h_matches, s.matches, (size_t)n_frames * blobs * 22, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(ctx, cudaMemcpyAsync(h_counter, s.counter, (size_t)n_frames * 12, cudaMemcpyDeviceToHost, ctx->stream));
+		StripPlan plan;
+		if (n_frames == 1 && ctx->strips > 1 && (p->fmt == VP_FMT_RGGB8 || p->fmt == VP_FMT_GRBG8) && is_pinned(ctx->lone, h_raw)) {
+			/* (a pageable frame is staged by the driver inside cudaMemcpyAsync: nothing to overlap with) */
+			/* the upload (5 MB, ~100 us of PCIe) is the longest step of a lone frame: cut it into chunks of raw rows on the
+			 * copy stream and let the row-local stages follow strip by strip on the compute stream */
+			rc = make_strip_plan(ctx, p, &plan);
+			if (rc) return rc;
+		}
+		/* results, counters and exactness flags come back in ONE download; the SAT bound is checked next to the record
+		 * kernel and a flagged frame (never seen on camera images) costs a second round trip instead of two idle launches
+		 * on every frame */
+		DetectOpts opts;
+		opts.flags = s.flags;
+		opts.defer_fallback = true;
+		if (plan.n > 1)
+			opts.plan = &plan;
+		const size_t res_bytes = s.off_matches + (size_t)n_frames * blobs * 22;
+
+		LoneFrameGraph& lg = ctx->lone;
+		bool replayed = false;
+		const bool graph_ok = ctx->latency_graph && n_frames == 1 && !ctx->profiling;
+		LoneFingerprint fp;
+		if (graph_ok) {
+			lone_fingerprint(ctx, s, p, &fp);
+			if (lg.exec && memcmp(&fp, &lg.fp, sizeof fp) != 0)
+				lg.reset();
+			if (!lg.exec && lg.have_fp && memcmp(&fp, &lg.fp, sizeof fp) == 0 && is_pinned(lg, h_raw)) {
+				/* second call in this configuration: everything is allocated, so the same enqueue can be captured */
+				rc = capture_lone_frame(ctx, s, h_raw, p, opts, raw_bytes, res_bytes);
+				if (rc) return rc;
+			}
+			if (lg.exec && (h_raw == lg.h_raw || is_pinned(lg, h_raw))) {
+				bool ok = true;
+				if (h_raw != lg.h_raw) { /* another buffer of the camera's ring: repoint the upload nodes */
+					for (const LoneFrameGraph::Upload& u : lg.uploads)
+						ok = ok && cudaGraphExecMemcpyNodeSetParams1D(lg.exec, u.node, s.raw + u.off, h_raw + u.off, u.bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+					lg.h_raw = h_raw;
+				}
+				if (ok) {
+					CK(ctx, cudaGraphLaunch(lg.exec, ctx->stream));
+					ctx->launches += lg.launches;
+					lg.replays++;
+					opts.deferred = lg.deferred;
+					replayed = true;
+				} else { /* could not be repointed: back to direct launches */
+					cudaGetLastError();
+					lg.reset();
+					lg.have_fp = false;
+				}
+			}
+		} else if (lg.exec || lg.have_fp) {
+			lg.reset();
+			lg.have_fp = false;
+		}
+		if (!replayed) {
+			rc = enqueue_lone_frames(ctx, s, h_raw, n_frames, p, opts, raw_bytes, res_bytes, false);
+			if (rc) return rc;
+			if (graph_ok && !lg.exec) { /* fingerprint AFTER the call: its first-use allocations are part of it */
+				lone_fingerprint(ctx, s, p, &lg.fp);
+				lg.have_fp = true;
+			}
+		}
 		ctx->last_flat = s.flat + (size_t)(n_frames - 1) * nf * 4;
 		ctx->last_grad = s.grad + (size_t)(n_frames - 1) * nf;
 		ctx->last_circ = s.circ + (size_t)(n_frames - 1) * nf;
-		CK(ctx, cudaStreamSynchronize(ctx->stream));
+		const int* const hflags = (const int*)(s.results_host + ((const uint8_t*)s.flags - s.results));
+		for (int round = 0;; round++) {
+			CK(ctx, cudaStreamSynchronize(ctx->stream));
+			int flagged = 0;
+			for (int i = 0; i < n_frames; i++)
+				flagged += hflags[i] != 0;
+			ctx->last_fallbacks = flagged;
+			if (!flagged || !opts.deferred || round == 1)
+				break;
+			rc = redo_flagged(ctx, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter, s.flags);
+			if (rc) return rc;
+			CK(ctx, cudaMemcpyAsync(s.results_host, s.results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+		}
+		memcpy(h_counter, s.results_host, (size_t)n_frames * 12);
+		for (int i = 0; i < n_frames && blobs; i++) { /* the valid records only; the rest of the caller's array keeps its contents */
+			const int32_t cnt = ((const int32_t*)s.results_host)[3 * i];
+			const size_t n_rec = cnt < 0 ? 0 : std::min((size_t)cnt, blobs);
+			memcpy((uint8_t*)h_matches + (size_t)i * blobs * 22, s.results_host + s.off_matches + (size_t)i * blobs * 22, n_rec * 22);
+		}
 		return VP_OK;
 	}
 	int k = 0;

@@ -151,6 +151,9 @@ def load() -> C.CDLL:
         "vp_ctx_set_group": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_lanes": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_hoist_chunk": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_strips": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_latency_graph": (C.c_int, [vp, C.c_int]),
+        "vp_latency_graph_replays": (C.c_uint64, [vp]),
         "vp_ctx_set_sat_free": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
@@ -452,6 +455,17 @@ class Context:
     def set_hoist_chunk(self, n: int):
         self._ck(self.lib.vp_ctx_set_hoist_chunk(self.h, n))
 
+    def set_strips(self, n: int):
+        """Chunks the upload of a lone frame is cut into on the latency path of detect_host (1 = no overlap)."""
+        self._ck(self.lib.vp_ctx_set_strips(self.h, n))
+
+    def set_latency_graph(self, on: bool):
+        """Replay the one-frame sequence of detect_host as a CUDA graph (default on)."""
+        self._ck(self.lib.vp_ctx_set_latency_graph(self.h, int(on)))
+
+    def latency_graph_replays(self) -> int:
+        return int(self.lib.vp_latency_graph_replays(self.h))
+
     def set_lanes(self, n: int):
         self._ck(self.lib.vp_ctx_set_lanes(self.h, n))
 
@@ -626,17 +640,26 @@ class Context:
         self._ck(self.lib.vp_detect_sat_fallbacks(self.h, C.byref(n)))
         return int(n.value)
 
-    def detect(self, raw: np.ndarray, p: Params, want_images: bool = True) -> dict:
+    def detect(self, raw: np.ndarray, p: Params, want_images: bool = True, pinned: bool = False) -> dict:
         """One or more frames through raw2quad + rgba2blobCenter + blobList (Resources.cpp:138-164, main.cpp:283-317).
 
-        raw: (n, raw_bytes) or a single frame.  Returns the blob lists (clamped to max_blobs like main.cpp:301),
+        raw: (n, raw_bytes) or a single frame; pinned=True stages it in pinned host memory first (the latency path of a
+        lone frame only overlaps the upload with the kernels for pinned frames).  Returns the blob lists (clamped to max_blobs like main.cpp:301),
         the counters, and -- for the last frame -- the `flat`, `gradDot`, `blobCenter` images."""
         rb = p.raw_frame_bytes()
         raw = np.ascontiguousarray(raw, np.uint8).reshape(-1, rb)
         n = raw.shape[0]
         matches = np.zeros((n, max(p.max_blobs, 1)), MATCH_DTYPE)
         counter = np.zeros((n, 3), np.int32)
-        self.detect_host_into(raw.ctypes.data, n, p, matches.ctypes.data, counter.ctypes.data)
+        if pinned:  # the frames in pinned host memory, like a camera driver's buffers: upload in strips, graph replay
+            ring = PinnedArray(raw.shape, np.uint8)
+            try:
+                ring.array[:] = raw
+                self.detect_host_into(ring.ptr.value, n, p, matches.ctypes.data, counter.ctypes.data)
+            finally:
+                ring.free()
+        else:
+            self.detect_host_into(raw.ctypes.data, n, p, matches.ctypes.data, counter.ctypes.data)
         out = {
             "matches": [matches[i, : min(int(counter[i, 0]), p.max_blobs)].copy() for i in range(n)],
             "counter": counter,
