@@ -2436,7 +2436,8 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 	if (rc[y] == 0)
 		return;
 	int before = 0;
-	for (int k = lane; k < y; k += 32)
+#pragma unroll 8
+	for (int k = lane; k < y; k += 32) /* independent loads: eight in flight (a lone frame waits on this chain) */
 		before += rc[k];
 #pragma unroll
 	for (int d = 16; d; d >>= 1)

@@ -1692,7 +1692,7 @@ int vp_detect_sat_fallbacks(vp_ctx* ctx, int* n)
 	return VP_OK;
 }
 
-/* Upload schedule of a lone frame for this geometry: tile rows are handed out in `strips` equal shares, and chunk k ends
+/* Upload schedule of a lone frame for this geometry: tile rows are handed out in `strips` shares, and chunk k ends
  * at the last raw row the tiles of share k read (known per geometry from the tile table, copied to the host once).  A
  * camera whose flat rows do not advance with the raw rows (rolled by 90 or 180 degrees) gets a plan whose first chunk is
  * most of the frame: still correct, just without the overlap.  plan->n = 0 when there is nothing to gain. */
@@ -1735,9 +1735,16 @@ static int make_strip_plan(vp_ctx* ctx, const vp_params* p, StripPlan* plan)
 	const int n = std::min(ctx->strips, tiles_y);
 	if (n < 2)
 		return VP_OK;
+	/* the last strip is what remains to be reprojected when the upload has ended: one wave of CTAs (2 per SM), the
+	 * shortest the kernel gets; the strips before it share the other tile rows evenly */
+	static const int last_env = getenv("VP_STRIP_LAST") ? atoi(getenv("VP_STRIP_LAST")) : 0; /* tuning aid: tile rows of the last strip */
+	int last_rows = last_env > 0 ? last_env : std::max(1, 2 * ctx->sm_count / tiles_x);
+	if (last_rows > tiles_y / n)
+		last_rows = tiles_y / n; /* never larger than an even share */
+	const int head_rows = tiles_y - last_rows;
 	int ty0 = 0, need = 0;
 	for (int k = 0; k < n; k++) {
-		const int ty1 = k == n - 1 ? tiles_y : (int)((long long)tiles_y * (k + 1) / n);
+		const int ty1 = k == n - 1 ? tiles_y : (int)((long long)head_rows * (k + 1) / (n - 1));
 		for (int ty = ty0; ty < ty1; ty++)
 			need = std::max(need, entry->rows_needed[ty]);
 		plan->ty_end[k] = ty1;
