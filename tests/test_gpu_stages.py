@@ -212,3 +212,32 @@ def test_batched_nv12_views_match_the_per_frame_calls(ctx, port):
             np.testing.assert_array_equal(got[i, :used], port.quad2nv12(ch, p.fmt, 0)[:used])
     with pytest.raises(lib.VpError):
         ctx.nv12_batch("rgba", rgba, w, h, stride=used - 2)              # stride smaller than a frame
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_wide_nv12_kernels_on_random_bytes(ctx, port, fmt):
+    """The 8x2-pixels-per-thread kernels (w % 8 == 0, aligned views): uniformly random bytes hit every rounding case of the
+    integer 16-bit-lane demosaic (ties of the 1/16 grid, both parities), the clamped left column and top row, and a
+    frame stride that leaves a gap."""
+    rng = np.random.default_rng(17 + fmt)
+    n, wq, hq = 3, 72, 46
+    raws = rng.integers(0, 256, (n, 4 * wq * hq), dtype=np.uint8)
+    raws[0, : 8 * wq] = np.tile(np.array([0, 255, 255, 0], np.uint8), 2 * wq)   # extremes next to each other
+    used = wq * hq * 3 // 2
+    stride = used + 72
+    got = ctx.nv12_batch("raw", raws, wq, hq, fmt=fmt, stride=stride)
+    for i in range(n):
+        ch = port.raw2quad(raws[i], fmt, wq, hq)
+        np.testing.assert_array_equal(got[i, :used], port.quad2nv12(ch, fmt, 0)[:used])
+        assert not got[i, used:].any()
+        np.testing.assert_array_equal(ctx.raw2nv12(raws[i], fmt, wq, hq, 0)[:used], got[i, :used])
+    rgba = rng.integers(0, 256, (n, hq, wq, 4), dtype=np.uint8)
+    f32 = (rng.standard_normal((n, hq, wq)) * 150).astype(np.float32)
+    f32[0, 0, :3] = [np.nan, np.inf, -np.inf]
+    got = ctx.nv12_batch("rgba", rgba, wq, hq, stride=stride)
+    for i in range(n):
+        np.testing.assert_array_equal(got[i, :used], port.rgba2nv12(rgba[i])[:used])
+        assert not got[i, used:].any()
+    got = ctx.nv12_batch("f32", f32, wq, hq, stride=stride)
+    for i in range(n):
+        np.testing.assert_array_equal(got[i, :used], port.f2nv12(f32[i])[:used])

@@ -2589,6 +2589,148 @@ __global__ void __launch_bounds__(256) k_f2nv12(const float* __restrict__ in, ui
 	*reinterpret_cast<uint16_t*>(out + (size_t)w * h + (size_t)by * w + 2 * bx) = (uint16_t)(127u | (127u << 8)); /* :25 */
 }
 
+/* ---- wide variants (w % 8 == 0, 8-byte aligned views): one thread per 8 x 2 pixels, 16-byte loads, 8-byte stores, a
+ * 1-D grid over (frame, block row, block column) so that no CTA is partly empty.  Same integer arithmetic as above. ---- */
+__device__ __forceinline__ uint32_t nv12_y_px(uint32_t rgba)
+{
+	/* 66 r + 129 g + 25 b as one byte dot product (alpha x 0); <= 56100, so the min of nv12_y never binds */
+	return (__dp4a(rgba, 0x00198142u, 0u) >> 8) + 16u;
+}
+__device__ __forceinline__ uint32_t nv12_uv_px(uint32_t rgba)
+{
+	return nv12_uv(rgba & 255u, (rgba >> 8) & 255u, (rgba >> 16) & 255u);
+}
+
+__global__ void __launch_bounds__(256) k_rgba2nv12_wide(const uint32_t* __restrict__ in, uint8_t* __restrict__ out, int w, int h, size_t in_stride,
+                                                        size_t out_stride, int n_frames)
+{
+	const int bw = w >> 3, bh = h >> 1;
+	const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (long long)bw * bh * n_frames)
+		return;
+	const int bx = (int)(idx % bw);
+	const long long t = idx / bw;
+	const int by = (int)(t % bh), f = (int)(t / bh);
+	const uint32_t* src = in + (size_t)f * in_stride + (size_t)(2 * by) * w + 8 * bx;
+	uint8_t* dst = out + (size_t)f * out_stride;
+	const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(src)), a1 = __ldg(reinterpret_cast<const uint4*>(src) + 1);
+	const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(src + w)), b1 = __ldg(reinterpret_cast<const uint4*>(src + w) + 1);
+	const uint32_t ya0 = nv12_y_px(a0.x) | (nv12_y_px(a0.y) << 8) | (nv12_y_px(a0.z) << 16) | (nv12_y_px(a0.w) << 24);
+	const uint32_t ya1 = nv12_y_px(a1.x) | (nv12_y_px(a1.y) << 8) | (nv12_y_px(a1.z) << 16) | (nv12_y_px(a1.w) << 24);
+	const uint32_t yb0 = nv12_y_px(b0.x) | (nv12_y_px(b0.y) << 8) | (nv12_y_px(b0.z) << 16) | (nv12_y_px(b0.w) << 24);
+	const uint32_t yb1 = nv12_y_px(b1.x) | (nv12_y_px(b1.y) << 8) | (nv12_y_px(b1.z) << 16) | (nv12_y_px(b1.w) << 24);
+	*reinterpret_cast<uint2*>(dst + (size_t)(2 * by) * w + 8 * bx) = make_uint2(ya0, ya1);
+	*reinterpret_cast<uint2*>(dst + (size_t)(2 * by + 1) * w + 8 * bx) = make_uint2(yb0, yb1);
+	/* UV of a 2x2 block from its bottom-right pixel (the last writer of rgba2nv12.cl:28-31 in raster order) */
+	*reinterpret_cast<uint2*>(dst + (size_t)w * h + (size_t)by * w + 8 * bx) =
+		make_uint2(nv12_uv_px(b0.y) | (nv12_uv_px(b0.w) << 16), nv12_uv_px(b1.y) | (nv12_uv_px(b1.w) << 16));
+}
+
+__global__ void __launch_bounds__(256) k_f2nv12_wide(const float* __restrict__ in, uint8_t* __restrict__ out, int w, int h, size_t in_stride,
+                                                     size_t out_stride, int n_frames)
+{
+	const int bw = w >> 3, bh = h >> 1;
+	const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (long long)bw * bh * n_frames)
+		return;
+	const int bx = (int)(idx % bw);
+	const long long t = idx / bw;
+	const int by = (int)(t % bh), f = (int)(t / bh);
+	const float* src = in + (size_t)f * in_stride + (size_t)(2 * by) * w + 8 * bx;
+	uint8_t* dst = out + (size_t)f * out_stride;
+	const float4 a0 = __ldg(reinterpret_cast<const float4*>(src)), a1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+	const float4 b0 = __ldg(reinterpret_cast<const float4*>(src + w)), b1 = __ldg(reinterpret_cast<const float4*>(src + w) + 1);
+#define VP_Y4(v) (f2y((v).x) | (f2y((v).y) << 8) | (f2y((v).z) << 16) | (f2y((v).w) << 24))
+	*reinterpret_cast<uint2*>(dst + (size_t)(2 * by) * w + 8 * bx) = make_uint2(VP_Y4(a0), VP_Y4(a1));
+	*reinterpret_cast<uint2*>(dst + (size_t)(2 * by + 1) * w + 8 * bx) = make_uint2(VP_Y4(b0), VP_Y4(b1));
+#undef VP_Y4
+	*reinterpret_cast<uint2*>(dst + (size_t)w * h + (size_t)by * w + 8 * bx) = make_uint2(0x7F7F7F7Fu, 0x7F7F7F7Fu); /* f2nv12.cl:25 */
+}
+
+/* quad2nv12.cl:23-58 straight from a Bayer frame, default sampling (bilinear, round-to-nearest-even), wq % 8 == 0.
+ *
+ * The sampler is asked for integer positions +-0.25 (quad2nv12.cl:36-40), so every filter weight is 0.25 or 0.75 against
+ * the texel to the left / above: plane c of pixel (x, y) is
+ *     [ wl*t(x-1,y-1) + wr*t(x,y-1) ] * wt + [ wl*t(x-1,y) + wr*t(x,y) ] * wb,   (wl,wr), (wt,wb) in {(1,3),(3,1)} / 4
+ * -- all products and sums are exact in fp32 (multiples of 1/16 below 256), so the float pipeline of the generic kernel
+ * computes S/16 exactly with S an integer <= 4080, and its round-to-nearest-even is (S + 7 + ((S >> 4) & 1)) >> 4.
+ * That integer form runs here on 16-bit lanes, two pixels per register: one thread = 8 x 2 output pixels from six 16-byte
+ * raw vectors (+ a 2-byte halo each), about 33 instructions per pixel instead of ~150.  Even bytes of a raw row are the
+ * planes tapped at x+0.25 (left 1, own 3), odd bytes those tapped at x-0.25 (left 3, own 1); even raw rows the planes
+ * tapped at y+0.25, odd rows those at y-0.25 (resampling.cl:65-70 / :74-80). */
+struct RawRowLanes {
+	uint32_t e[4], o[4]; /* horizontally blended even-byte / odd-byte plane: word j = pixels (x0+2j, x0+2j+1), 16-bit lanes, <= 1020 */
+};
+__device__ __forceinline__ RawRowLanes raw_row_hblend(const uint8_t* __restrict__ row, int x0)
+{
+	const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + 2 * x0));
+	const uint32_t halo = x0 > 0 ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + 2 * x0 - 2)) : (v.x & 0xFFFFu); /* quad x0-1, clamped to quad 0 */
+	const uint32_t wd[4] = { v.x, v.y, v.z, v.w };
+	RawRowLanes r;
+	uint32_t pe = (halo & 0xFFu) << 16, po = (halo >> 8) << 16; /* "previous word": the left neighbour sits in its high lane */
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		const uint32_t ce = wd[j] & 0x00FF00FFu, co = __byte_perm(wd[j], 0u, 0x4341);
+		const uint32_t le = __byte_perm(pe, ce, 0x5432), lo = __byte_perm(po, co, 0x5432); /* (t(x-1), t(x)) of the word's two pixels */
+		r.e[j] = 3u * ce + le; /* x + 0.25: left 1/4, own 3/4 */
+		r.o[j] = 3u * lo + co; /* x - 0.25: left 3/4, own 1/4 */
+		pe = ce;
+		po = co;
+	}
+	return r;
+}
+/* (S + 7 + ((S >> 4) & 1)) >> 4 on both lanes; the bits the word-wide shift drags across are left for the caller to mask */
+__device__ __forceinline__ uint32_t rte16_lanes(uint32_t s) { return (s + 0x00070007u + ((s >> 4) & 0x00010001u)) >> 4; }
+
+template <int FMT>
+__global__ void __launch_bounds__(256) k_raw2nv12_wide(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, int wq, int hq, size_t src_stride,
+                                                       size_t out_stride, int n_frames)
+{
+	const int bw = wq >> 3, bh = hq >> 1;
+	const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (long long)bw * bh * n_frames)
+		return;
+	const int bx = (int)(idx % bw);
+	const long long t = idx / bw;
+	const int by = (int)(t % bh), f = (int)(t / bh);
+	const uint8_t* src = raw + (size_t)f * src_stride;
+	uint8_t* dst = out + (size_t)f * out_stride;
+	const int x0 = 8 * bx, rb = 2 * wq;
+	const int qrow[3] = { max(2 * by - 1, 0), 2 * by, 2 * by + 1 };
+	RawRowLanes top_e = raw_row_hblend(src + (size_t)(2 * qrow[0]) * rb, x0); /* planes 0 | 1 of the quad row above */
+	RawRowLanes top_o = raw_row_hblend(src + (size_t)(2 * qrow[0] + 1) * rb, x0); /* planes 2 | 3 */
+	uint32_t uvw[4];
+#pragma unroll
+	for (int k = 0; k < 2; k++) {
+		const RawRowLanes own_e = raw_row_hblend(src + (size_t)(2 * qrow[k + 1]) * rb, x0);
+		const RawRowLanes own_o = raw_row_hblend(src + (size_t)(2 * qrow[k + 1] + 1) * rb, x0);
+		uint32_t yw[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			/* y + 0.25 (even raw rows): above 1/4, own 3/4; y - 0.25 (odd raw rows): above 3/4, own 1/4 */
+			const uint32_t v0 = rte16_lanes(3u * own_e.e[j] + top_e.e[j]), v1 = rte16_lanes(3u * own_e.o[j] + top_e.o[j]);
+			const uint32_t v2 = rte16_lanes(3u * top_o.e[j] + own_o.e[j]), v3 = rte16_lanes(3u * top_o.o[j] + own_o.o[j]);
+			uint32_t r, g, b;
+			if (FMT == FMT_RGGB) { /* g = v1 / 2 + v2 / 2: even lanes add without a carry and the shift brings in a zero */
+				r = v0 & 0x00FF00FFu;
+				g = ((v1 & 0x00FE00FEu) + (v2 & 0x00FE00FEu)) >> 1;
+				b = v3 & 0x00FF00FFu;
+			} else {
+				r = v1 & 0x00FF00FFu;
+				g = ((v0 & 0x00FE00FEu) + (v3 & 0x00FE00FEu)) >> 1;
+				b = v2 & 0x00FF00FFu;
+			}
+			yw[j] = (((66u * r + (129u * g + 25u * b)) >> 8) & 0x00FF00FFu) + 0x00100010u; /* <= 56100 per lane: no carry; rgba2nv12.cl:27 */
+			if (k == 1) /* UV of the 2x2 block from its bottom-right pixel: the high lane of the lower row */
+				uvw[j] = nv12_uv(r >> 16, g >> 16, b >> 16);
+		}
+		*reinterpret_cast<uint2*>(dst + (size_t)qrow[k + 1] * wq + x0) = make_uint2(__byte_perm(yw[0], yw[1], 0x6420), __byte_perm(yw[2], yw[3], 0x6420));
+		top_e = own_e;
+		top_o = own_o;
+	}
+	*reinterpret_cast<uint2*>(dst + (size_t)wq * hq + (size_t)by * wq + x0) = make_uint2(uvw[0] | (uvw[1] << 16), uvw[2] | (uvw[3] << 16));
+}
+
 template <int FMT, int MODE, class Src>
 __global__ void __launch_bounds__(256) k_quad2nv12(Src s0, uint8_t* __restrict__ out, int wq, int hq, size_t src_stride = 0, size_t out_stride = 0)
 {

@@ -1098,6 +1098,33 @@ static int check_nv12(vp_ctx* ctx, int w, int h, const vp_buf* nv12)
 	return VP_OK;
 }
 
+/* the wide NV12 kernels want 16-byte aligned source rows and 8-byte aligned destination rows */
+static bool nv12_wide_ok(const void* in, const void* out, int w, int h, size_t out_stride)
+{
+	static const bool off = getenv("VP_NV12_WIDE") && atoi(getenv("VP_NV12_WIDE")) == 0; /* A/B aid: the one-thread-per-2x2-block kernels */
+	return !off && (w % 8) == 0 && (h % 2) == 0 && ((uintptr_t)in % 16) == 0 && ((uintptr_t)out % 8) == 0 && (out_stride % 8) == 0;
+}
+
+static int launch_rgba2nv12(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_t* d_nv12, int n, size_t out_stride)
+{
+	if (nv12_wide_ok(d_rgba, d_nv12, w, h, out_stride)) {
+		const long long n_thr = (long long)(w / 8) * (h / 2) * n;
+		k_rgba2nv12_wide<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h, (size_t)w * h, out_stride, n);
+	} else
+		k_rgba2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h, (size_t)w * h, out_stride);
+	return check_launch(ctx, "k_rgba2nv12");
+}
+
+static int launch_f2nv12(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_nv12, int n, size_t out_stride)
+{
+	if (nv12_wide_ok(d_f32, d_nv12, w, h, out_stride)) {
+		const long long n_thr = (long long)(w / 8) * (h / 2) * n;
+		k_f2nv12_wide<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h, (size_t)w * h, out_stride, n);
+	} else
+		k_f2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h, (size_t)w * h, out_stride);
+	return check_launch(ctx, "k_f2nv12");
+}
+
 int vp_rgba2nv12_device(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_t* d_nv12)
 {
 	REQUIRE(ctx, ctx && d_rgba && d_nv12, "null argument");
@@ -1105,8 +1132,7 @@ int vp_rgba2nv12_device(vp_ctx* ctx, const uint8_t* d_rgba, int w, int h, uint8_
 	if (w == 0 || h == 0) return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
 	Stage st(ctx, "rgba2nv12");
-	k_rgba2nv12<<<dim3(cdiv(w / 2, 256), h / 2), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h);
-	return check_launch(ctx, "k_rgba2nv12");
+	return launch_rgba2nv12(ctx, d_rgba, w, h, d_nv12, 1, 0);
 }
 
 int vp_f2nv12_device(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_nv12)
@@ -1116,8 +1142,7 @@ int vp_f2nv12_device(vp_ctx* ctx, const float* d_f32, int w, int h, uint8_t* d_n
 	if (w == 0 || h == 0) return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
 	Stage st(ctx, "f2nv12");
-	k_f2nv12<<<dim3(cdiv(w / 2, 256), h / 2), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h);
-	return check_launch(ctx, "k_f2nv12");
+	return launch_f2nv12(ctx, d_f32, w, h, d_nv12, 1, 0);
 }
 
 int vp_rgba2nv12(vp_ctx* ctx, const vp_img* rgba, vp_buf* nv12)
@@ -1170,6 +1195,15 @@ static int raw_src_launch_nv12(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int w
 		SrcBGR s{ d_raw, wq };
 		return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq, n, src_stride, out_stride);
 	}
+	if (mode == VP_SAMPLE_BILINEAR_RTE && nv12_wide_ok(d_raw, out, wq, hq, out_stride)) {
+		/* default sampling, aligned rows: the integer 16-bit-lane kernel (bit-identical, see k_raw2nv12_wide) */
+		const long long n_thr = (long long)(wq / 8) * (hq / 2) * n;
+		if (fmt == VP_FMT_RGGB8)
+			k_raw2nv12_wide<FMT_RGGB><<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(d_raw, out, wq, hq, src_stride, out_stride, n);
+		else
+			k_raw2nv12_wide<FMT_GRBG><<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(d_raw, out, wq, hq, src_stride, out_stride, n);
+		return check_launch(ctx, "k_raw2nv12_wide");
+	}
 	SrcBayer s{ d_raw, 2 * wq };
 	return launch_quad2nv12(ctx, s, fmt, mode, out, wq, hq, n, src_stride, out_stride);
 }
@@ -1192,8 +1226,7 @@ int vp_rgba2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_rgba, int n_frames, 
 	if (n_frames == 0 || w == 0 || h == 0) return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
 	Stage st(ctx, "rgba2nv12");
-	k_rgba2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n_frames), 256, 0, ctx->stream>>>((const uint32_t*)d_rgba, d_nv12, w, h, (size_t)w * h, nv12_stride);
-	return check_launch(ctx, "k_rgba2nv12");
+	return launch_rgba2nv12(ctx, d_rgba, w, h, d_nv12, n_frames, nv12_stride);
 }
 
 int vp_f2nv12_batch_device(vp_ctx* ctx, const float* d_f32, int n_frames, int w, int h, uint8_t* d_nv12, size_t nv12_stride)
@@ -1203,8 +1236,7 @@ int vp_f2nv12_batch_device(vp_ctx* ctx, const float* d_f32, int n_frames, int w,
 	if (n_frames == 0 || w == 0 || h == 0) return VP_OK;
 	CK(ctx, cudaSetDevice(ctx->device));
 	Stage st(ctx, "f2nv12");
-	k_f2nv12<<<dim3(cdiv(w / 2, 256), h / 2, n_frames), 256, 0, ctx->stream>>>(d_f32, d_nv12, w, h, (size_t)w * h, nv12_stride);
-	return check_launch(ctx, "k_f2nv12");
+	return launch_f2nv12(ctx, d_f32, w, h, d_nv12, n_frames, nv12_stride);
 }
 
 int vp_raw2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, int fmt, int wq, int hq, uint8_t* d_nv12, size_t nv12_stride, int mode)
