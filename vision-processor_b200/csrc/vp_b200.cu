@@ -82,7 +82,6 @@ struct LoneFrameGraph {
 	const uint8_t* h_raw = nullptr; /* frame address the upload nodes currently point at */
 	struct Upload { cudaGraphNode_t node; size_t off, bytes; };
 	std::vector<Upload> uploads;
-	std::vector<const void*> pinned; /* frame addresses already checked to be pinned host memory */
 	bool deferred = false;
 	uint64_t launches = 0;    /* kernels one replay launches */
 	uint64_t replays = 0;
@@ -1887,22 +1886,15 @@ static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p,
 	memcpy(fp->knob, knobs, sizeof knobs);
 }
 
-static bool is_pinned(LoneFrameGraph& lg, const void* host)
+/* asked on every call (~1 us): an address that was pinned once may have been freed and handed out again as pageable memory */
+static bool is_pinned(LoneFrameGraph&, const void* host)
 {
-	for (const void* q : lg.pinned)
-		if (q == host)
-			return true;
 	cudaPointerAttributes a;
 	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
 		cudaGetLastError();
 		return false;
 	}
-	if (a.type != cudaMemoryTypeHost)
-		return false;
-	if (lg.pinned.size() >= 64)
-		lg.pinned.clear();
-	lg.pinned.push_back(host);
-	return true;
+	return a.type == cudaMemoryTypeHost;
 }
 
 /* capture one lone-frame enqueue (copy stream forked from and joined back into the compute stream) and instantiate it;
@@ -1989,7 +1981,8 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 		/* latency path (a camera delivering one frame at a time) */
 		HostSlot& s = ctx->slots[0];
 		StripPlan plan;
-		if (n_frames == 1 && ctx->strips > 1 && (p->fmt == VP_FMT_RGGB8 || p->fmt == VP_FMT_GRBG8) && is_pinned(ctx->lone, h_raw)) {
+		const bool pinned = n_frames == 1 && is_pinned(ctx->lone, h_raw);
+		if (pinned && ctx->strips > 1 && (p->fmt == VP_FMT_RGGB8 || p->fmt == VP_FMT_GRBG8)) {
 			/* (a pageable frame is staged by the driver inside cudaMemcpyAsync: nothing to overlap with) */
 			/* the upload (5 MB, ~100 us of PCIe) is the longest step of a lone frame: cut it into chunks of raw rows on the
 			 * copy stream and let the row-local stages follow strip by strip on the compute stream */
@@ -2014,12 +2007,12 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 			lone_fingerprint(ctx, s, p, &fp);
 			if (lg.exec && memcmp(&fp, &lg.fp, sizeof fp) != 0)
 				lg.reset();
-			if (!lg.exec && lg.have_fp && memcmp(&fp, &lg.fp, sizeof fp) == 0 && is_pinned(lg, h_raw)) {
+			if (!lg.exec && lg.have_fp && memcmp(&fp, &lg.fp, sizeof fp) == 0 && pinned) {
 				/* second call in this configuration: everything is allocated, so the same enqueue can be captured */
 				rc = capture_lone_frame(ctx, s, h_raw, p, opts, raw_bytes, res_bytes);
 				if (rc) return rc;
 			}
-			if (lg.exec && (h_raw == lg.h_raw || is_pinned(lg, h_raw))) {
+			if (lg.exec && pinned) {
 				bool ok = true;
 				if (h_raw != lg.h_raw) { /* another buffer of the camera's ring: repoint the upload nodes */
 					for (const LoneFrameGraph::Upload& u : lg.uploads)
