@@ -349,13 +349,16 @@ def main():
 
     # ---- single-frame latency through the host API (p50 / p99) ------------------------------------
     lat = []
+    replays0 = ctx.latency_graph_replays()
     for i in range(300):
         t0 = time.perf_counter()
         ctx.detect_host_into(pin_raw.ptr.value + (i % Be) * rb, 1, p, pin_m.ptr.value, pin_c.ptr.value)
         lat.append(1e3 * (time.perf_counter() - t0))
     lat = np.sort(np.array(lat[20:]))
     latency = {"p50_ms": float(lat[len(lat) // 2]), "p99_ms": float(lat[int(len(lat) * 0.99)]), "frames": int(len(lat)),
-               "path": "vp_detect_host, 1 frame per call, pinned host in -> host blob list out"}
+               "path": "vp_detect_host, 1 frame per call, pinned host in -> host blob list out; upload in 2 chunks of rows with the "
+                       "reprojection of the first under the second, one download, replayed as a CUDA graph",
+               "graph_replays": int(ctx.latency_graph_replays() - replays0)}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
