@@ -23,6 +23,44 @@ namespace {
 
 thread_local std::string t_last_error;
 
+/* Pinned host ranges handed out by this library (vp_host_alloc, the host mirrors of vp_buf): a frame inside one of them is
+ * known to be pinned without asking the driver -- cudaPointerGetAttributes costs several microseconds per call, which the
+ * latency path cannot afford on every frame.  Anything else (memory the caller pinned itself) is asked. */
+std::mutex g_pinned_mu;
+std::vector<std::pair<uintptr_t, size_t>> g_pinned;
+
+void pinned_register(const void* p, size_t bytes)
+{
+	std::lock_guard<std::mutex> l(g_pinned_mu);
+	g_pinned.emplace_back((uintptr_t)p, bytes);
+}
+void pinned_unregister(const void* p)
+{
+	std::lock_guard<std::mutex> l(g_pinned_mu);
+	for (size_t i = 0; i < g_pinned.size(); i++)
+		if (g_pinned[i].first == (uintptr_t)p) {
+			g_pinned[i] = g_pinned.back();
+			g_pinned.pop_back();
+			return;
+		}
+}
+bool is_pinned(const void* host, size_t bytes)
+{
+	{
+		std::lock_guard<std::mutex> l(g_pinned_mu);
+		const uintptr_t a = (uintptr_t)host;
+		for (const auto& r : g_pinned)
+			if (a >= r.first && a + bytes <= r.first + r.second)
+				return true;
+	}
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
 struct LutEntry {
 	uint8_t key[104];
 	float2* d = nullptr;
@@ -821,6 +859,7 @@ int vp_buf_alloc(vp_ctx* ctx, size_t bytes, vp_buf** out)
 		delete b;
 		return fail(ctx, VP_ERR_NOMEM, "buffer allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
 	}
+	pinned_register(b->h, alloc);
 	*out = b;
 	return VP_OK;
 }
@@ -854,6 +893,7 @@ int vp_buf_release(vp_buf* b)
 	cudaSetDevice(b->ctx->device);
 	cudaStreamSynchronize(b->ctx->stream);
 	cudaFree(b->d);
+	pinned_unregister(b->h);
 	cudaFreeHost(b->h);
 	delete b;
 	return VP_OK;
@@ -1886,17 +1926,6 @@ static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p,
 	memcpy(fp->knob, knobs, sizeof knobs);
 }
 
-/* asked on every call (~1 us): an address that was pinned once may have been freed and handed out again as pageable memory */
-static bool is_pinned(LoneFrameGraph&, const void* host)
-{
-	cudaPointerAttributes a;
-	if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
-		cudaGetLastError();
-		return false;
-	}
-	return a.type == cudaMemoryTypeHost;
-}
-
 /* capture one lone-frame enqueue (copy stream forked from and joined back into the compute stream) and instantiate it;
  * on any failure the capture is abandoned and the caller carries on with direct launches */
 static int capture_lone_frame(vp_ctx* ctx, HostSlot& s, const uint8_t* h_raw, const vp_params* p, const DetectOpts& opts, size_t raw_bytes, size_t res_bytes)
@@ -1981,7 +2010,7 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 		/* latency path (a camera delivering one frame at a time) */
 		HostSlot& s = ctx->slots[0];
 		StripPlan plan;
-		const bool pinned = n_frames == 1 && is_pinned(ctx->lone, h_raw);
+		const bool pinned = n_frames == 1 && is_pinned(h_raw, raw_bytes);
 		if (pinned && ctx->strips > 1 && (p->fmt == VP_FMT_RGGB8 || p->fmt == VP_FMT_GRBG8)) {
 			/* (a pageable frame is staged by the driver inside cudaMemcpyAsync: nothing to overlap with) */
 			/* the upload (5 MB, ~100 us of PCIe) is the longest step of a lone frame: cut it into chunks of raw rows on the
@@ -2129,11 +2158,14 @@ int vp_host_alloc(size_t bytes, void** out)
 	cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
 	if (e != cudaSuccess)
 		return fail(nullptr, VP_ERR_NOMEM, "pinned allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+	pinned_register(*out, bytes ? bytes : 1);
 	return VP_OK;
 }
 
 int vp_host_free(void* p)
 {
+	if (p)
+		pinned_unregister(p);
 	if (p && cudaFreeHost(p) != cudaSuccess)
 		return fail(nullptr, VP_ERR_CUDA, "cudaFreeHost failed");
 	return VP_OK;
