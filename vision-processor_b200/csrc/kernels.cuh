@@ -858,9 +858,27 @@ __global__ void __launch_bounds__(1024 / PX, 2) k_reproject_hoist(const uint8_t*
  * of the four frames' raw vectors: 2 PRMT per staged word) and stores a quarter of the bytes.  The arithmetic per frame is
  * unchanged -- same operations in the same order on the same values: bit-identical to k_reproject_hoist.
  *
- * Pipeline per quad of frames: copy(q+1) in flight (cp.async, own vectors) | convert(q) -> T | barrier | blend(q) | barrier.
+ * Pipeline per quad of frames: convert(q) -> T | copy(q+1) issued (cp.async, own vectors, lands under the blend) | barrier | blend(q) | barrier.
  * ---------------------------------------------------------------------------------------------- */
-constexpr size_t HOIST4_SMEM = (size_t)HT * 4 + 2 * 4 * (size_t)HRING;
+/* build-time A/B (profiles/r01_hoist_sweeps.txt): stages of the raw ring -- 1 (default): a thread refills its ring slots right
+ * after converting them, the copy of quad q+1 flies under blend(q); 2: the copy is issued one step earlier, for 31 KB more
+ * shared memory per CTA (measured 2 % slower) -- and CTAs per SM the register allocation is sized for (3 = 80 registers
+ * with 55 values spilled: measured 15 % slower than 2) */
+#ifndef VP_HOIST4_STAGES
+#define VP_HOIST4_STAGES 1
+#endif
+#ifndef VP_HOIST4_CTAS
+#define VP_HOIST4_CTAS 2
+#endif
+/* build-time A/B: keep the eight axis values of a pixel in registers and form the sixteen weights in the blend (default:
+ * 32 instead of 64 registers of frame-invariant state and 16 more FMUL per pixel and quad of frames; the registers it frees
+ * go to instruction-level parallelism -- the kernel waits on dependent chains at 4 warps per scheduler -- measured 3 % faster;
+ * a third CTA per SM on top of it, 80 registers with 68 B spilled, measured slower again) */
+#ifndef VP_HOIST4_AXES
+#define VP_HOIST4_AXES 1
+#endif
+constexpr int HOIST4_STAGES = VP_HOIST4_STAGES;
+constexpr size_t HOIST4_SMEM = (size_t)HT * 4 + HOIST4_STAGES * 4 * (size_t)HRING;
 
 /* w * (byte LO, byte LO+1) of a staged word as ONE packed FMA on the biased floats 2^23 + b (0x4B0000bb):
  * fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once, i.e. bit for bit mul.rn(w, float(b)); wm = -w * 2^23
@@ -875,7 +893,7 @@ __device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w, float wm)
 }
 
 template <int FMT, bool FULL>
-__device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][8], const int (&O)[4][4], uint32_t* __restrict__ out,
+__device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][VP_HOIST4_AXES ? 4 : 8], const int (&O)[4][4], uint32_t* __restrict__ out,
                                              uint32_t nfl, int wf, bool okx, int rows_ok, int n_valid, unsigned long long one2)
 {
 #pragma unroll
@@ -888,8 +906,17 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 #pragma unroll
 			for (int tap = 0; tap < 4; tap++) {
 				const uint32_t wd = t[(tap & 1) + (tap >> 1) * HP];
+#if VP_HOIST4_AXES
+				/* W[k] holds the eight axis values of the pixel (ox, ax, oyp, ayp | oyn, ayn): the weight is formed here, with the
+				 * same single rounding as in the setup of the 64-register variant */
+				const float2 xw = W[k][tap & 1];                                   /* (+0.25 axis, -0.25 axis): ox for tap 0/2, ax for tap 1/3 */
+				const float2 yw = W[k][2 + (tap >> 1)];                            /* (y axis of channels 0/1, y axis of channels 2/3): oy, ay */
+				float w; /* volatile: the product is frame-invariant and would be hoisted out of the frame loop again (64 registers) */
+				asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(w) : "f"((c & 1) ? xw.y : xw.x), "f"((c >> 1) ? yw.y : yw.x));
+#else
 				const float2 wp = W[k][4 * (c >> 1) + tap];
 				const float w = (c & 1) ? wp.y : wp.x;
+#endif
 				const float wm = __fmul_rn(w, -8388608.0f);
 				const float2 pab = weighted_pair<0>(wd, w, wm);
 				const float2 pcd = weighted_pair<2>(wd, w, wm);
@@ -916,7 +943,7 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+__global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
                                                                const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq,
                                                                int wf, int hf, int n_frames, int chunk, float one)
 {
@@ -995,7 +1022,7 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __re
 	const uint8_t* next_src = raw; /* first frame of the next quad to copy */
 	auto issue_copy = [&](int q) { /* frames 4q..4q+3 (the last frame repeated past the end) into stage q & 1; always commits */
 		if (vec && q < n_quads) {
-			unsigned char* dst = my_ring + (q & 1) * 4 * HRING;
+			unsigned char* dst = my_ring + (q % HOIST4_STAGES) * 4 * HRING;
 			const int left = n - 4 * q; /* >= 1 */
 			const uint8_t* src = next_src;
 #pragma unroll
@@ -1020,7 +1047,7 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __re
 				uint32_t fr[4][4];
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
-					uint4 qq = *reinterpret_cast<const uint4*>(my_ring + ((q & 1) * 4 + j) * HRING + i * 4096);
+					uint4 qq = *reinterpret_cast<const uint4*>(my_ring + ((q % HOIST4_STAGES) * 4 + j) * HRING + i * 4096);
 					if (s_edge[i]) { /* replicate the edge quad's two bytes over the whole vector */
 						const uint32_t eq = s_edge[i] == 1 ? (qq.x & 0xFFFFu) : (qq.w >> 16);
 						qq.x = qq.y = qq.z = qq.w = eq * 0x00010001u;
@@ -1062,7 +1089,7 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __re
 	issue_copy(0);
 
 	/* ---- frame-invariant part: weights and tap offsets of this thread's four pixels (the first copy is in flight) ---- */
-	float2 W[4][8];
+	float2 W[4][VP_HOIST4_AXES ? 4 : 8];
 	int O[4][4];
 	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
 #pragma unroll
@@ -1075,8 +1102,13 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __re
 		axis_staged2(add2(make_float2(pos[k].y, pos[k].y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
 		const float2 ayp = make_float2(ay.x, ay.x), oyp = make_float2(oy.x, oy.x);
 		const float2 ayn = make_float2(ay.y, ay.y), oyn = make_float2(oy.y, oy.y);
+#if VP_HOIST4_AXES
+		W[k][0] = ox; W[k][1] = ax; W[k][2] = oy; W[k][3] = ay; /* oy = (oyp, oyn), ay = (ayp, ayn) */
+		(void)oyp; (void)ayp; (void)oyn; (void)ayn;
+#else
 		W[k][0] = mul2(ox, oyp); W[k][1] = mul2(ax, oyp); W[k][2] = mul2(ox, ayp); W[k][3] = mul2(ax, ayp);
 		W[k][4] = mul2(ox, oyn); W[k][5] = mul2(ax, oyn); W[k][6] = mul2(ox, ayn); W[k][7] = mul2(ax, ayn);
+#endif
 		O[k][0] = ok ? iyp * HP + ixp : 0; /* pixels outside the image read texel 0 and are not stored */
 		O[k][1] = ok ? HPLANE + iyp * HP + ixn : 0;
 		O[k][2] = ok ? 2 * HPLANE + iyn * HP + ixp : 0;
@@ -1090,9 +1122,15 @@ __global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __re
 
 #pragma unroll 1
 	for (int q = 0; q < n_quads; q++) {
-		issue_copy(q + 1);
-		cp_async_wait<1>(); /* quad q has landed (this thread's vectors) */
-		convert(q);
+		if (HOIST4_STAGES == 2) {
+			issue_copy(q + 1);
+			cp_async_wait<1>(); /* quad q has landed (this thread's vectors) */
+			convert(q);
+		} else { /* one stage: a thread refills its own ring slots as soon as it has converted them */
+			cp_async_wait<0>();
+			convert(q);
+			issue_copy(q + 1);
+		}
 		__syncthreads();
 		const int n_valid = min(4, n - 4 * q);
 		if (full)

@@ -125,6 +125,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("VPB200_LIB"):  # A/B builds of the same library (tools); never a fallback
+        LIB_PATH = os.environ["VPB200_LIB"]
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           f"(make -C vision-processor_b200/csrc).  vpb200 has no CPU fallback.")
