@@ -1442,7 +1442,11 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	const bool defer_fallback = opts.defer_fallback && sat_free && n_groups == 1; /* only the SAT-free flow has a check to move */
 	opts.deferred = defer_fallback;
 
-	{
+	/* scratch of the compaction (blob masks, row counts, counters, flags) cleared for the whole batch up front -- or, when
+	 * the batch runs as several groups, group by group at the head of each group's lane, so that clearing overlaps the other
+	 * lanes' kernels instead of standing alone before the fork */
+	const bool prepare_per_group = n_groups > 1 && !fused_sat;
+	if (!prepare_per_group) {
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
 		/* enough CTAs to clear the blob masks of a lone frame in one pass (the kernel strides over them) */
@@ -1514,6 +1518,13 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 		int32_t* counter = d_counter + 3 * (size_t)f0;
 		int32_t* rowcount = ctx->rowcount + (size_t)f0 * hf;
 		uint32_t* masks = ctx->masks + (size_t)f0 * hf * wpr;
+		if (prepare_per_group) {
+			Stage st(ctx, "prepare", 1, s);
+			const int n = g * hf;
+			const int prep_ctas = std::max(cdiv(n, 256), std::min(cdiv(n * wpr, 256), 4 * ctx->sm_count));
+			k_peaks_prepare<<<prep_ctas, 256, 0, s>>>(counter, ctx->first_slot + f0, rowcount, n, g, 1, flag, masks, n * wpr);
+			if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
+		}
 		if (!by_strips) {
 			Stage st(ctx, "reproject", 1, s);
 			if (hoisted) {
