@@ -877,8 +877,15 @@ __global__ void __launch_bounds__(1024 / PX, 2) k_reproject_hoist(const uint8_t*
 #ifndef VP_HOIST4_AXES
 #define VP_HOIST4_AXES 1
 #endif
+/* build-time A/B: plane buffers.  2: quad q+1 is converted into the other buffer while slower warps still blend quad q,
+ * ONE barrier per quad instead of two -- measured 3 % slower than 1 (32 KB more shared memory per CTA, i.e. less L1 for
+ * the coordinate table and the raw vectors; the barrier wait it removes was not the limiter) */
+#ifndef VP_HOIST4_TBUF
+#define VP_HOIST4_TBUF 1
+#endif
 constexpr int HOIST4_STAGES = VP_HOIST4_STAGES;
-constexpr size_t HOIST4_SMEM = (size_t)HT * 4 + HOIST4_STAGES * 4 * (size_t)HRING;
+constexpr int HOIST4_TBUF = VP_HOIST4_TBUF;
+constexpr size_t HOIST4_SMEM = HOIST4_TBUF * (size_t)HT * 4 + HOIST4_STAGES * 4 * (size_t)HRING;
 
 /* w * (byte LO, byte LO+1) of a staged word as ONE packed FMA on the biased floats 2^23 + b (0x4B0000bb):
  * fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once, i.e. bit for bit mul.rn(w, float(b)); wm = -w * 2^23
@@ -948,8 +955,8 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
                                                                int wf, int hf, int n_frames, int chunk, float one)
 {
 	extern __shared__ __align__(16) unsigned char hoist_smem[];
-	uint32_t* const T = reinterpret_cast<uint32_t*>(hoist_smem);
-	unsigned char* const ring = hoist_smem + (size_t)HT * 4;
+	uint32_t* const T0 = reinterpret_cast<uint32_t*>(hoist_smem);
+	unsigned char* const ring = hoist_smem + HOIST4_TBUF * (size_t)HT * 4;
 	const int tx = blockIdx.x, ty = blockIdx.y;
 	const int f0 = blockIdx.z * chunk;
 	const int n = min(n_frames, f0 + chunk) - f0;
@@ -1039,6 +1046,7 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 		cp_async_commit();
 	};
 	auto convert = [&](int q) { /* this thread's vectors of quad q: byte transpose of the four frames -> T */
+		uint32_t* const T = T0 + (HOIST4_TBUF == 2 ? (q & 1) * HT : 0);
 		if (vec) {
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
@@ -1132,13 +1140,17 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 			issue_copy(q + 1);
 		}
 		__syncthreads();
+		const uint32_t* const T = T0 + (HOIST4_TBUF == 2 ? (q & 1) * HT : 0);
 		const int n_valid = min(4, n - 4 * q);
 		if (full)
 			hoist4_blend<FMT, true>(T, W, O, out, nfl, wf, true, 16, n_valid, one2);
 		else
 			hoist4_blend<FMT, false>(T, W, O, out, nfl, wf, okx, rows_ok, n_valid, one2);
 		out += (size_t)4 * nfl;
-		__syncthreads(); /* everybody has read T before the next quad is converted into it */
+		if (HOIST4_TBUF == 1)
+			__syncthreads(); /* everybody has read T before the next quad is converted into it */
+		/* two buffers: quad q+1 goes into the other one, which was last read by blend(q-1) -- and every warp had left that
+		 * before it passed this iteration's barrier */
 	}
 }
 
