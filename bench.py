@@ -33,6 +33,7 @@ from vpb200 import geometry as G, synth as S  # noqa: E402
 SENSOR_W, SENSOR_H = 2448, 2048
 METRIC = "2448x2048 Bayer frames/sec (full detection pipeline, aggregate over GPUs)"
 UNIT = "frames/s"
+WORKLOAD = "single camera 2448x2048 BayerRG8 full detection pipeline (BASELINE configs[1]); one camera stream per GPU"
 
 
 # ------------------------------------------------------------------------------------------------ workload
@@ -158,7 +159,7 @@ def run_reference(args, rank: int):
     emit(({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32/f32",
-        "data": "synthetic", "config": {"workload": "single camera 2448x2048 BayerRG8 full detection pipeline", "frames_per_step": per_step},
+        "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -364,7 +365,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32/f32", "data": "synthetic",
-        "config": {"workload": "single camera 2448x2048 BayerRG8 full detection pipeline (BASELINE configs[1]); one camera stream per GPU",
+        "config": {"workload": WORKLOAD,
                    "frames_per_step_per_gpu": B, "flat_size": [lp.wf, lp.hf], "max_blobs": p.max_blobs, "blobs_per_frame": blobs_per_frame,
                    "l2": f"inputs larger than L2: {B} frames x {rb} B = {B * rb / 1e6:.0f} MB raw per step, streamed from HBM every step",
                    "parallelism": f"{world} independent camera streams, no collective",
