@@ -276,7 +276,9 @@ VP_API int vp_raw2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_fra
 VP_API int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes);
 VP_API int vp_copy_to_device(vp_ctx* ctx, void* dev, const void* host, size_t bytes);
 
-/* pinned host memory for frame sources (the camera drivers' user buffers, spinnakerdriver.cpp:120-133) */
+/* pinned host memory for frame sources (the camera drivers' user buffers, spinnakerdriver.cpp:120-133).  Frames inside
+ * memory from vp_host_alloc (or inside a mapped vp_buf) are known to be pinned without a driver query; a frame the caller
+ * pinned by other means is recognised too, at the price of one cudaPointerGetAttributes (~5 us) per one-frame call */
 VP_API int vp_host_alloc(size_t bytes, void** out);
 VP_API int vp_host_free(void* p);
 

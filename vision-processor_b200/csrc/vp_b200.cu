@@ -1894,14 +1894,8 @@ static int enqueue_lone_frames(vp_ctx* ctx, HostSlot& s, const uint8_t* h_raw, i
 		/* everything in order on one stream, no cross-stream hops */
 		CK(ctx, cudaMemcpyAsync(s.raw, h_raw, (size_t)n_frames * raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
 	}
-	static const bool upload_only = getenv("VP_DEBUG_UPLOAD_ONLY") != nullptr; /* measurement aid: the copies alone (results are stale) */
-	if (upload_only) {
-		if (opts.plan)
-			CK(ctx, cudaStreamWaitEvent(ctx->stream, opts.plan->uploaded[opts.plan->n - 1], 0));
-	} else {
-		int rc = detect_batch_impl(ctx, s.raw, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter, opts);
-		if (rc) return rc;
-	}
+	int rc = detect_batch_impl(ctx, s.raw, n_frames, p, s.flat, s.grad, s.circ, s.matches, s.counter, opts);
+	if (rc) return rc;
 	CK(ctx, cudaMemcpyAsync(s.results_host, s.results, res_bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	return VP_OK;
 }
