@@ -231,6 +231,9 @@ def test_wide_nv12_kernels_on_random_bytes(ctx, port, fmt):
         np.testing.assert_array_equal(got[i, :used], port.quad2nv12(ch, fmt, 0)[:used])
         assert not got[i, used:].any()
         np.testing.assert_array_equal(ctx.raw2nv12(raws[i], fmt, wq, hq, 0)[:used], got[i, :used])
+        np.testing.assert_array_equal(ctx.raw2rgba(raws[i], fmt, wq, hq, 0), port.quad2rgba(ch, fmt, 0))
+        odd = raws[i][: 4 * wq * (hq - 1)]                                       # an odd number of quad rows
+        np.testing.assert_array_equal(ctx.raw2rgba(odd, fmt, wq, hq - 1, 0), port.quad2rgba(port.raw2quad(odd, fmt, wq, hq - 1), fmt, 0))
     rgba = rng.integers(0, 256, (n, hq, wq, 4), dtype=np.uint8)
     f32 = (rng.standard_normal((n, hq, wq)) * 150).astype(np.float32)
     f32[0, 0, :3] = [np.nan, np.inf, -np.inf]

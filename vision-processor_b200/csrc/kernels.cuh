@@ -2732,6 +2732,53 @@ __device__ __forceinline__ RawRowLanes raw_row_hblend(const uint8_t* __restrict_
 /* (S + 7 + ((S >> 4) & 1)) >> 4 on both lanes; the bits the word-wide shift drags across are left for the caller to mask */
 __device__ __forceinline__ uint32_t rte16_lanes(uint32_t s) { return (s + 0x00070007u + ((s >> 4) & 0x00010001u)) >> 4; }
 
+/* r, g, b of the two pixels of word j (16-bit lanes, 0..255) from the horizontally blended raw rows of the quad row above
+ * (top_e: planes 0|1, top_o: planes 2|3) and of the own quad row */
+template <int FMT>
+__device__ __forceinline__ void demosaic_lanes(const RawRowLanes& top_e, const RawRowLanes& top_o, const RawRowLanes& own_e, const RawRowLanes& own_o, int j,
+                                               uint32_t& r, uint32_t& g, uint32_t& b)
+{
+	/* y + 0.25 (even raw rows): above 1/4, own 3/4; y - 0.25 (odd raw rows): above 3/4, own 1/4 */
+	const uint32_t v0 = rte16_lanes(3u * own_e.e[j] + top_e.e[j]), v1 = rte16_lanes(3u * own_e.o[j] + top_e.o[j]);
+	const uint32_t v2 = rte16_lanes(3u * top_o.e[j] + own_o.e[j]), v3 = rte16_lanes(3u * top_o.o[j] + own_o.o[j]);
+	if (FMT == FMT_RGGB) { /* g = v1 / 2 + v2 / 2: even lanes add without a carry and the shift brings in a zero */
+		r = v0 & 0x00FF00FFu;
+		g = ((v1 & 0x00FE00FEu) + (v2 & 0x00FE00FEu)) >> 1;
+		b = v3 & 0x00FF00FFu;
+	} else {
+		r = v1 & 0x00FF00FFu;
+		g = ((v0 & 0x00FE00FEu) + (v3 & 0x00FE00FEu)) >> 1;
+		b = v2 & 0x00FF00FFu;
+	}
+}
+
+/* quad2rgba.cl:23-53 straight from a Bayer frame, default sampling, wq % 8 == 0: the same integer demosaic, one thread per
+ * 8 x 1 pixels, written as RGBA8 (two 16-byte stores) */
+template <int FMT>
+__global__ void __launch_bounds__(256) k_raw2rgba_wide(const uint8_t* __restrict__ raw, uint32_t* __restrict__ out, int wq, int hq)
+{
+	const int bw = wq >> 3;
+	const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+	if (idx >= (long long)bw * hq)
+		return;
+	const int bx = (int)(idx % bw), y = (int)(idx / bw);
+	const int x0 = 8 * bx, rb = 2 * wq, ya = max(y - 1, 0);
+	const RawRowLanes top_e = raw_row_hblend(raw + (size_t)(2 * ya) * rb, x0), top_o = raw_row_hblend(raw + (size_t)(2 * ya + 1) * rb, x0);
+	const RawRowLanes own_e = raw_row_hblend(raw + (size_t)(2 * y) * rb, x0), own_o = raw_row_hblend(raw + (size_t)(2 * y + 1) * rb, x0);
+	uint32_t px[8];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		uint32_t r, g, b;
+		demosaic_lanes<FMT>(top_e, top_o, own_e, own_o, j, r, g, b);
+		const uint32_t rg = __byte_perm(r, g, 0x6240), ba = b | 0xFF00FF00u; /* (r0, g0, r1, g1), (b0, 255, b1, 255) */
+		px[2 * j] = __byte_perm(rg, ba, 0x5410);     /* quad2rgba.cl:52 */
+		px[2 * j + 1] = __byte_perm(rg, ba, 0x7632);
+	}
+	uint4* o = reinterpret_cast<uint4*>(out + (size_t)y * wq + x0);
+	o[0] = make_uint4(px[0], px[1], px[2], px[3]);
+	o[1] = make_uint4(px[4], px[5], px[6], px[7]);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) k_raw2nv12_wide(const uint8_t* __restrict__ raw, uint8_t* __restrict__ out, int wq, int hq, size_t src_stride,
                                                        size_t out_stride, int n_frames)
@@ -2757,19 +2804,8 @@ __global__ void __launch_bounds__(256) k_raw2nv12_wide(const uint8_t* __restrict
 		uint32_t yw[4];
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
-			/* y + 0.25 (even raw rows): above 1/4, own 3/4; y - 0.25 (odd raw rows): above 3/4, own 1/4 */
-			const uint32_t v0 = rte16_lanes(3u * own_e.e[j] + top_e.e[j]), v1 = rte16_lanes(3u * own_e.o[j] + top_e.o[j]);
-			const uint32_t v2 = rte16_lanes(3u * top_o.e[j] + own_o.e[j]), v3 = rte16_lanes(3u * top_o.o[j] + own_o.o[j]);
 			uint32_t r, g, b;
-			if (FMT == FMT_RGGB) { /* g = v1 / 2 + v2 / 2: even lanes add without a carry and the shift brings in a zero */
-				r = v0 & 0x00FF00FFu;
-				g = ((v1 & 0x00FE00FEu) + (v2 & 0x00FE00FEu)) >> 1;
-				b = v3 & 0x00FF00FFu;
-			} else {
-				r = v1 & 0x00FF00FFu;
-				g = ((v0 & 0x00FE00FEu) + (v3 & 0x00FE00FEu)) >> 1;
-				b = v2 & 0x00FF00FFu;
-			}
+			demosaic_lanes<FMT>(top_e, top_o, own_e, own_o, j, r, g, b);
 			yw[j] = (((66u * r + (129u * g + 25u * b)) >> 8) & 0x00FF00FFu) + 0x00100010u; /* <= 56100 per lane: no carry; rgba2nv12.cl:27 */
 			if (k == 1) /* UV of the 2x2 block from its bottom-right pixel: the high lane of the lower row */
 				uvw[j] = nv12_uv(r >> 16, g >> 16, b >> 16);

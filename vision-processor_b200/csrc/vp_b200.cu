@@ -1310,6 +1310,15 @@ int vp_raw2rgba_device(vp_ctx* ctx, const uint8_t* d_raw, int fmt, int wq, int h
 		SrcBGR s{ d_raw, wq };
 		return launch_quad2rgba(ctx, s, fmt, mode, (uint32_t*)d_rgba, wq, hq);
 	}
+	if (mode == VP_SAMPLE_BILINEAR_RTE && nv12_wide_ok(d_raw, d_rgba, wq, 2, 0) && ((uintptr_t)d_rgba % 16) == 0) {
+		/* default sampling, aligned rows: the integer 16-bit-lane demosaic (bit-identical, see k_raw2nv12_wide) */
+		const long long n_thr = (long long)(wq / 8) * hq;
+		if (fmt == VP_FMT_RGGB8)
+			k_raw2rgba_wide<FMT_RGGB><<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(d_raw, (uint32_t*)d_rgba, wq, hq);
+		else
+			k_raw2rgba_wide<FMT_GRBG><<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(d_raw, (uint32_t*)d_rgba, wq, hq);
+		return check_launch(ctx, "k_raw2rgba_wide");
+	}
 	SrcBayer s{ d_raw, 2 * wq };
 	return launch_quad2rgba(ctx, s, fmt, mode, (uint32_t*)d_rgba, wq, hq);
 }
