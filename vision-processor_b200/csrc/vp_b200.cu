@@ -1843,6 +1843,10 @@ static int make_strip_plan(vp_ctx* ctx, const vp_params* p, StripPlan* plan)
 		plan->uploaded[k] = ctx->strip_uploaded[k];
 		ty0 = ty1;
 	}
+	/* nothing to overlap when the first share already needs (almost) the whole frame: a camera rolled against the flat
+	 * image's row order.  One upload, one launch then. */
+	if ((long long)plan->raw_end[0] * 10 >= (long long)H * 9)
+		return VP_OK;
 	plan->n = n;
 	return VP_OK;
 }
