@@ -25,13 +25,16 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--strips", default="1,2,4,6,8,12")
 ap.add_argument("--frames", type=int, default=300)
 ap.add_argument("--no-graph", action="store_true", help="direct launches instead of the CUDA graph replay")
+ap.add_argument("--ring", type=int, default=4, help="pinned frame buffers the calls rotate through (1 = always the same address)")
 args = ap.parse_args()
 
 lp, frames = bench.build_workload(4)
+args.ring = max(1, min(args.ring, 32))
 p = lib.params_from_launch(lp)
 rb = p.raw_frame_bytes()
-pin_raw = lib.PinnedArray((4, rb), np.uint8)
-pin_raw.array[:] = frames
+pin_raw = lib.PinnedArray((args.ring, rb), np.uint8)
+for i in range(args.ring):
+    pin_raw.array[i] = frames[i % 4]
 pin_m = lib.PinnedArray((p.max_blobs * 22,), np.uint8)
 pin_c = lib.PinnedArray((1, 3), np.int32)
 
@@ -44,7 +47,7 @@ with lib.Context(0) as ctx:
         r0 = ctx.latency_graph_replays()
         for i in range(args.frames + 20):
             t0 = time.perf_counter()
-            ctx.detect_host_into(pin_raw.ptr.value + (i % 4) * rb, 1, p, pin_m.ptr.value, pin_c.ptr.value)
+            ctx.detect_host_into(pin_raw.ptr.value + (i % args.ring) * rb, 1, p, pin_m.ptr.value, pin_c.ptr.value)
             lat.append(1e3 * (time.perf_counter() - t0))
         lat = np.sort(np.array(lat[20:]))
         got = (pin_c.array.copy().tolist(), pin_m.array[: 22 * min(int(pin_c.array[0, 0]), p.max_blobs)].tobytes())
@@ -52,4 +55,4 @@ with lib.Context(0) as ctx:
             ref = got
         same = got == ref
         print(json.dumps({"strips": n, "p50_ms": round(float(lat[len(lat) // 2]), 4), "p99_ms": round(float(lat[int(len(lat) * 0.99)]), 4),
-                          "min_ms": round(float(lat[0]), 4), "counter": got[0], "same_as_first": same, "graph_replays": ctx.latency_graph_replays() - r0}), flush=True)
+                          "min_ms": round(float(lat[0]), 4), "counter": got[0], "same_as_first": same, "graph_replays": ctx.latency_graph_replays() - r0, "ring": args.ring}), flush=True)
