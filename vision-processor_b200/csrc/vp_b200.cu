@@ -562,12 +562,20 @@ __global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict_
 	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
 }
 
-/* rows per CTA of the streaming circularity kernels: 128 for batches (few halo rows per segment); a lone frame has only
- * hf/128 x 14 CTAs to offer, so shorter segments trade halo work for shorter dependent chains and a full GPU */
-int circ_seg_rows(int n_frames)
+/* rows per CTA of the streaming circularity kernels: 128 (few halo rows per segment) whenever that already gives the GPU two
+ * CTAs per SM; fewer frames or smaller images take 64 or 32 rows and trade halo work for shorter dependent chains and a
+ * full GPU (a lone 1224x1024 frame has only 14 x 8 CTAs to offer at 128 rows) */
+int circ_seg_rows(const vp_ctx* ctx, int wf, int hf, int n_frames, int r)
 {
 	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
-	return seg_env > 0 ? seg_env : (n_frames >= 3 ? 128 : 32);
+	if (seg_env > 0)
+		return seg_env;
+	const int swu = 32 - (r + 2) - 1; /* output columns per warp, see k_circ_stream_rs */
+	const long long per_row_of_segments = (long long)cdiv(cdiv(wf, swu > 0 ? swu : 1), 4) * n_frames;
+	for (int seg = 128; seg > 32; seg >>= 1)
+		if (per_row_of_segments * cdiv(hf, seg) >= 2LL * ctx->sm_count)
+			return seg;
+	return 32;
 }
 
 int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
@@ -1386,7 +1394,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
-	const int seg = circ_seg_rows(n_frames);
+	const int seg = circ_seg_rows(ctx, wf, hf, n_frames, p->circle_radius);
 	const int n_seg = cdiv(hf, seg);
 	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
 	if (sat_free) {
@@ -1729,7 +1737,7 @@ static int redo_flagged(vp_ctx* ctx, int n_frames, const vp_params* p, uint8_t* 
                         int32_t* d_counter, int* flags)
 {
 	const int wf = p->wf, hf = p->hf, wpr = cdiv(wf, 32);
-	const int seg = circ_seg_rows(n_frames), n_seg = cdiv(hf, seg), r = p->circle_radius;
+	const int r = p->circle_radius, seg = circ_seg_rows(ctx, wf, hf, n_frames, r), n_seg = cdiv(hf, seg);
 	const int ns = need_score(p->circ_threshold, p->min_score);
 	cudaStream_t s = ctx->stream;
 	uint32_t* flat = (uint32_t*)d_flat;
