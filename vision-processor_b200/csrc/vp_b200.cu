@@ -2038,9 +2038,9 @@ int vp_detect_host(vp_ctx* ctx, const uint8_t* h_raw, int n_frames, const vp_par
 		StripPlan plan;
 		const bool pinned = n_frames == 1 && is_pinned(h_raw, raw_bytes);
 		if (pinned && ctx->strips > 1 && (p->fmt == VP_FMT_RGGB8 || p->fmt == VP_FMT_GRBG8)) {
-			/* (a pageable frame is staged by the driver inside cudaMemcpyAsync: nothing to overlap with) */
-			/* the upload (5 MB, ~100 us of PCIe) is the longest step of a lone frame: cut it into chunks of raw rows on the
-			 * copy stream and let the row-local stages follow strip by strip on the compute stream */
+			/* the upload (5 MB, ~100 us of PCIe) is the longest step of a lone frame: cut it into chunks of raw rows on the copy
+			 * stream and reproject the flat rows a chunk completes while the next one is still on its way (a pageable frame
+			 * is staged by the driver inside cudaMemcpyAsync: nothing to overlap with) */
 			rc = make_strip_plan(ctx, p, &plan);
 			if (rc) return rc;
 		}
