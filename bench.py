@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=96, help="frames per step and per GPU")
+    ap.add_argument("--batch", type=int, default=192, help="frames per step and per GPU (three groups of 64 frames on three streams)")
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = automatic)")
     ap.add_argument("--lanes", type=int, default=0, help="streams the groups are spread over (0 = library default)")

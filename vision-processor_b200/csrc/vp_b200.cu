@@ -586,11 +586,14 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 	 * few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set
 	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau.  Three lanes (streams) with one group each in flight
 	 * cover the launch gaps and tails of one group with the other groups' kernels (profiles/r01_group_sweep.txt). */
-	size_t g = (size_t)40 * 1024 * 1024 / nf;
+	size_t g = (size_t)80 * 1024 * 1024 / nf; /* 64 frames of 1224x1024: 10.44 us/frame against 10.61 at 32 (profiles/r01_group_sweep.txt) */
 	if (g < 1) g = 1;
 	if (g > 64) g = 64;
 	const size_t per_lane = ((size_t)n_frames + lanes - 1) / lanes;
 	if (g > per_lane) g = per_lane;
+	/* whole chunks of the hoisted reprojection (16 frames per CTA, 4 per shared-memory word): a group of 33 frames would
+	 * end in a slice of one frame that pays the full per-tile setup (measured: 5.17 instead of 4.89 us/frame) */
+	if (g >= 16) g -= g % 16;
 	return (int)g;
 }
 
