@@ -584,7 +584,7 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 		return ctx->group < n_frames ? ctx->group : n_frames;
 	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over a
 	 * few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set
-	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau.  Three lanes (streams) with one group each in flight
+	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau, ~80 Mpx another 2 % up with the final kernels.  Three lanes (streams) with one group each in flight
 	 * cover the launch gaps and tails of one group with the other groups' kernels (profiles/r01_group_sweep.txt). */
 	size_t g = (size_t)80 * 1024 * 1024 / nf; /* 64 frames of 1224x1024: 10.44 us/frame against 10.61 at 32 (profiles/r01_group_sweep.txt) */
 	if (g < 1) g = 1;
