@@ -292,7 +292,7 @@ VP_API int vp_ctx_set_lanes(vp_ctx* ctx, int lanes);
  * derived per frame), 2 (default) = staged kernel that keeps the frame-invariant weights of a tile in registers over a
  * chunk of frames of the batch */
 VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
-/* tuning knob of variant 2: frames of a launch group one CTA processes with the same registers (0 = automatic: 8, fewer
+/* tuning knob of variant 2: frames of a launch group one CTA processes with the same registers (0 = automatic: 32, fewer
  * when the grid would not fill the GPU) */
 VP_API int vp_ctx_set_hoist_chunk(vp_ctx* ctx, int frames);
 /* latency knob of vp_detect_host with ONE pinned frame (a camera delivering frame by frame, src/main.cpp:262-289): the

@@ -1549,7 +1549,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			Stage st(ctx, "reproject", 1, s);
 			if (hoisted) {
 				/* one CTA keeps a tile's weights in registers for `chunk` frames; enough CTAs to fill the GPU several times */
-				int chunk = ctx->hoist_chunk > 0 ? ctx->hoist_chunk : 16;
+				int chunk = ctx->hoist_chunk > 0 ? ctx->hoist_chunk : 32; /* 32 at 64-frame groups: 10.46 against 10.56 us/frame at 16 (profiles/r01_group_sweep.txt) */
 				const long long tiles_per_frame = (long long)cdiv(wf, FT_W) * cdiv(hf, FT_H);
 				while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
