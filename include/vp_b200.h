@@ -225,6 +225,9 @@ VP_API int vp_blob_score(vp_ctx* ctx, const vp_img* rgba, const vp_img* circ, vp
  *   d_circ     n_frames x wf*hf    F32       (`blobCenter`)
  *   d_matches  n_frames x max_blobs*22 bytes
  *   d_counter  n_frames x 3 int32            (zeroed by the call)
+ * Alignment contract: d_raw, d_flat, d_grad and d_circ must be 16-byte aligned (the kernels move them as 16-byte vectors;
+ * anything from cudaMalloc / vp_buf_alloc / a torch tensor's data_ptr at offset 0 is), d_counter 4-byte, d_matches 2-byte;
+ * a misaligned pointer is refused with VP_ERR_INVALID before anything is launched.
  * Asynchronous on the context stream. */
 VP_API int vp_detect_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, const vp_params* params,
                                   uint8_t* d_flat, float* d_grad, float* d_circ,
@@ -317,6 +320,14 @@ VP_API int vp_ctx_set_sat_free(vp_ctx* ctx, int on);
 /* A/B switch (default OFF: measured 6.8 vs 5.8 us/frame on B200): gradient + summed-area table in one pass (strip-resident in shared memory, aggregate
  * look-back between strips) vs gradient+row scan followed by a column scan; results are bit-identical */
 VP_API int vp_ctx_set_fused_sat(vp_ctx* ctx, int on);
+
+/* what the most recent fused call (vp_detect_batch_device / vp_detect_host) actually launched, for tests and sweeps that
+ * must know which specialised kernel they exercised: plan[0] reprojection kernel (0 direct gather, 1 staged per frame,
+ * 2 frame-invariant one frame per word, 4 frame-invariant four frames per word), plan[1] frames per CTA of that kernel,
+ * plan[2] frames per launch group, plan[3] streams used, plan[4] circularity path (0 unfused generic radius, 1 tiled from
+ * the SAT, 2 streaming from the SAT, 3 streaming from row sums, 4 fused gradient + circularity), plan[5] rows per
+ * circularity segment, plan[6] 1 when the reprojection staged its tiles with TMA, plan[7] reserved */
+VP_API int vp_detect_last_plan(const vp_ctx* ctx, int32_t plan[8]);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 VP_API uint64_t vp_launch_count(const vp_ctx* ctx);

@@ -87,3 +87,44 @@ def assert_float_images_equal(a: np.ndarray, b: np.ndarray):
     np.testing.assert_array_equal(a[fin].view(np.uint32), b[fin].view(np.uint32))
     inf = ~fin & ~np.isnan(a)
     np.testing.assert_array_equal(a[inf], b[inf])
+
+
+def detect_device(ctx, frames, vp, images=("flat", "grad", "circ")):
+    """`frames` (n raw frames) through vp_detect_batch_device with device-resident buffers; returns every frame's images,
+    counters and 22-byte records, and what the call launched (ctx.last_plan())."""
+    from vpb200 import lib
+    frames = np.ascontiguousarray(np.stack(frames), np.uint8)
+    n, rb = frames.shape
+    nf = vp.wf * vp.hf
+    bufs = dict(raw=ctx.buffer(n * rb, frames), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
+                m=ctx.buffer(n * max(vp.max_blobs, 1) * 22), c=ctx.buffer(n * 12))
+    try:
+        ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
+                                bufs["m"].device_ptr, bufs["c"].device_ptr)
+        out = dict(plan=ctx.last_plan(), sat_fallbacks=ctx.sat_fallbacks())
+        if "flat" in images:
+            out["flat"] = bufs["flat"].read(np.uint8).reshape(n, vp.hf, vp.wf, 4)
+        if "grad" in images:
+            out["grad"] = bufs["grad"].read(np.float32).reshape(n, vp.hf, vp.wf)
+        if "circ" in images:
+            out["circ"] = bufs["circ"].read(np.float32).reshape(n, vp.hf, vp.wf)
+        counter = bufs["c"].read(np.int32).reshape(n, 3)
+        m = bufs["m"].read(np.uint8).reshape(n, max(vp.max_blobs, 1), 22)
+        out["counter"] = counter
+        out["matches"] = [m[i, : min(int(counter[i, 0]), vp.max_blobs)].copy().view(lib.MATCH_DTYPE).reshape(-1) for i in range(n)]
+    finally:
+        for b in bufs.values():
+            b.release()
+    return out
+
+
+def assert_frame_equal(got, i, want, images=("flat", "grad", "circ")):
+    """Frame i of a detect_device() result against one oracle result: images bit for bit, counters, records."""
+    if "flat" in images:
+        np.testing.assert_array_equal(got["flat"][i], want["flat"])
+    if "grad" in images:
+        np.testing.assert_array_equal(got["grad"][i], want["grad"])
+    if "circ" in images:
+        assert_float_images_equal(got["circ"][i], want["circ"])
+    np.testing.assert_array_equal(got["counter"][i], want["counter"])
+    assert_matches_equal(got["matches"][i], want["matches"])

@@ -148,13 +148,19 @@ def test_hoisted_reprojection_over_frame_chunks(ctx, port, chunk, kw):
     bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
                 m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
     ctx.set_hoist_chunk(chunk)
+    ctx.set_lanes(1)
+    ctx.set_group(n)
     try:
         ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
                                 bufs["m"].device_ptr, bufs["c"].device_ptr)
         flat = bufs["flat"].read(np.uint8).reshape(n, p.hf, p.wf, 4)
         counter = bufs["c"].read(np.int32).reshape(n, 3)
+        plan = ctx.last_plan()
     finally:
         ctx.set_hoist_chunk(0)
+        ctx.set_group(0)
+        ctx.set_lanes(3)
+    assert plan["chunk"] == chunk and plan["group"] == n and plan["reproject"] == (4 if chunk >= 4 else 2)
     for i, w in enumerate(wants):
         np.testing.assert_array_equal(flat[i], w["flat"])
         np.testing.assert_array_equal(counter[i], w["counter"])
@@ -489,7 +495,7 @@ def test_four_frame_reprojection_on_unusual_geometry(ctx, port, scale_mul, dx, d
     tiny, or lies partly/entirely outside the sensor (edge replication in the byte transpose): five frames, chunk 4."""
     frames = []
     for s_ in range(5):
-        p, raw, _ = common.make_case(wq=320, hq=200, fmt=s_ % 1, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=30 + s_)
+        p, raw, _ = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=30 + s_)
         frames.append(raw)
     p.field_scale *= scale_mul
     p.off_x += dx

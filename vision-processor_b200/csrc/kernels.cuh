@@ -2475,7 +2475,13 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 	const int f = blockIdx.y;
 	const int n_row_ctas = (h + 7) >> 3;
 	if (blockIdx.x >= n_row_ctas) { /* only launched when segsum is given: one thread per column */
-		if (flag[f] == 0 && sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w) && threadIdx.x == 0)
+		/* the sibling column CTAs of this frame may raise the flag while this one runs: the CTA takes ONE snapshot, so that
+		 * every warp reaches the barrier inside sat_bound_exceeded or none does */
+		__shared__ int flag_seen;
+		if (threadIdx.x == 0)
+			flag_seen = flag[f];
+		__syncthreads();
+		if (flag_seen == 0 && sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w) && threadIdx.x == 0)
 			flag[f] = 2;
 		return;
 	}

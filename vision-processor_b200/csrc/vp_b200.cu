@@ -183,6 +183,7 @@ struct vp_ctx {
 	size_t sync_cap = 0;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
+	int32_t last_plan[8] = {}; /* vp_detect_last_plan */
 
 	cudaEvent_t strip_uploaded[MAX_STRIPS] = {};
 	cudaEvent_t strip_flat[1] = {}; /* all strips reprojected */
@@ -750,6 +751,14 @@ int vp_ctx_sync(vp_ctx* ctx)
 }
 
 void* vp_ctx_stream(vp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int vp_detect_last_plan(const vp_ctx* ctx, int32_t plan[8])
+{
+	if (!ctx || !plan)
+		return fail(nullptr, VP_ERR_INVALID, "null argument");
+	memcpy(plan, ctx->last_plan, sizeof ctx->last_plan);
+	return VP_OK;
+}
 uint64_t vp_launch_count(const vp_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group) /* tuning knob used by the benchmark sweep; 0 = automatic */
@@ -1385,6 +1394,13 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	REQUIRE(ctx, n_frames >= 0, "negative frame count");
 	if (n_frames == 0) return VP_OK;
 	REQUIRE(ctx, d_raw && d_flat && d_grad && d_circ && d_counter && (d_matches || p->max_blobs == 0), "null device pointer");
+	/* the fused kernels move raw rows, flat pixels, gradients and circularities as 16-byte vectors (cp.async / TMA boxes, uint4
+	 * and float4 accesses): a misaligned base would fault inside a kernel, which is a sticky error that takes the context
+	 * down, so it is refused here (cudaMalloc and vp_buf memory is 256-byte aligned; frame strides are multiples of 16
+	 * whenever the vector paths are taken) */
+	REQUIRE(ctx, ((((uintptr_t)d_raw) | ((uintptr_t)d_flat) | ((uintptr_t)d_grad) | ((uintptr_t)d_circ)) & 15u) == 0,
+	        "d_raw, d_flat, d_grad and d_circ must be 16-byte aligned");
+	REQUIRE(ctx, (((uintptr_t)d_counter) & 3u) == 0 && (((uintptr_t)d_matches) & 1u) == 0, "d_counter must be 4-byte and d_matches 2-byte aligned");
 	CK(ctx, cudaSetDevice(ctx->device));
 	const int wf = p->wf, hf = p->hf;
 	const size_t nf = (size_t)wf * hf;
@@ -1461,6 +1477,14 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	int* const flags = opts.flags ? opts.flags : ctx->flag;
 	const bool defer_fallback = opts.defer_fallback && sat_free && n_groups == 1; /* only the SAT-free flow has a check to move */
 	opts.deferred = defer_fallback;
+	int32_t* const plan_out = ctx->last_plan;
+	plan_out[0] = hoisted ? 2 : staged ? 1 : 0;
+	plan_out[1] = 1;
+	plan_out[2] = G;
+	plan_out[3] = lanes;
+	plan_out[4] = sat_free ? 3 : fused_circ ? (ctx->stream_circ ? 2 : 1) : 0;
+	plan_out[5] = seg;
+	plan_out[6] = plan_out[7] = 0;
 
 	/* scratch of the compaction (blob masks, row counts, counters, flags) cleared for the whole batch up front -- or, when
 	 * the batch runs as several groups, group by group at the head of each group's lane, so that clearing overlaps the other
@@ -1551,7 +1575,8 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 				/* one CTA keeps a tile's weights in registers for `chunk` frames; enough CTAs to fill the GPU several times */
 				int chunk = ctx->hoist_chunk > 0 ? ctx->hoist_chunk : 32; /* 32 at 64-frame groups: 10.46 against 10.56 us/frame at 16 (profiles/r01_group_sweep.txt) */
 				const long long tiles_per_frame = (long long)cdiv(wf, FT_W) * cdiv(hf, FT_H);
-				while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
+				if (ctx->hoist_chunk <= 0) /* an explicit vp_ctx_set_hoist_chunk is taken as it is (tests, sweeps) */
+					while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
 				static const size_t hoist_pad = getenv("VP_HOIST_PAD") ? (size_t)atoi(getenv("VP_HOIST_PAD")) : 0; /* tuning aid: caps residency */
 				const size_t HOIST_SMEM_L = HOIST_SMEM + hoist_pad;
@@ -1564,7 +1589,9 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 					ctx->hoist_attr = true;
 				}
 				static const int hoist_quads = getenv("VP_HOIST_QUADS") ? atoi(getenv("VP_HOIST_QUADS")) : 1; /* tuning aid / A-B */
+				plan_out[1] = chunk;
 				if (hoist_px == 4 && hoist_quads && chunk >= 4) {
+					plan_out[0] = 4;
 					if (!ctx->hoist4_attr) {
 						CK(ctx, cudaFuncSetAttribute(k_reproject_hoist4<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST4_SMEM));
 						CK(ctx, cudaFuncSetAttribute(k_reproject_hoist4<FMT_GRBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST4_SMEM));
@@ -1866,6 +1893,13 @@ static int ensure_slots(vp_ctx* ctx, size_t frames, size_t raw_bytes, size_t nf,
 {
 	if (frames <= ctx->slot_frames && raw_bytes <= ctx->slot_raw && nf <= ctx->slot_nf && blobs <= ctx->slot_blobs)
 		return VP_OK;
+	/* every capacity only ever grows: alternating call shapes (few frames with many blobs, many frames with few) settle on
+	 * the envelope after one reallocation each instead of reallocating -- three stream syncs, fifteen allocations and a
+	 * dropped lone-frame graph -- on every call */
+	frames = std::max(frames, ctx->slot_frames);
+	raw_bytes = std::max(raw_bytes, ctx->slot_raw);
+	nf = std::max(nf, ctx->slot_nf);
+	blobs = std::max(blobs, ctx->slot_blobs);
 	CK(ctx, cudaStreamSynchronize(ctx->stream));
 	CK(ctx, cudaStreamSynchronize(ctx->copy_in));
 	CK(ctx, cudaStreamSynchronize(ctx->copy_out));

@@ -162,6 +162,7 @@ def load() -> C.CDLL:
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
+        "vp_detect_last_plan": (C.c_int, [vp, C.POINTER(C.c_int32)]),
         "vp_profiling_enable": (C.c_int, [vp, C.c_int]),
         "vp_profiling_count": (C.c_int, [vp]),
         "vp_profiling_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
@@ -457,6 +458,12 @@ class Context:
 
     def set_hoist_chunk(self, n: int):
         self._ck(self.lib.vp_ctx_set_hoist_chunk(self.h, n))
+
+    def last_plan(self) -> dict:
+        """What the most recent fused call launched (vp_detect_last_plan): which specialised kernels a test really exercised."""
+        a = (C.c_int32 * 8)()
+        self._ck(self.lib.vp_detect_last_plan(self.h, a))
+        return dict(reproject=a[0], chunk=a[1], group=a[2], lanes=a[3], circ=a[4], seg_rows=a[5], tma=a[6])
 
     def set_strips(self, n: int):
         """Chunks the upload of a lone frame is cut into on the latency path of detect_host (1 = no overlap)."""
