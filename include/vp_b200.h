@@ -310,6 +310,10 @@ VP_API int vp_ctx_set_strips(vp_ctx* ctx, int strips);
 VP_API int vp_ctx_set_latency_graph(vp_ctx* ctx, int on);
 /* one-frame calls of vp_detect_host served by a graph replay so far (tests, tools) */
 VP_API uint64_t vp_latency_graph_replays(const vp_ctx* ctx);
+/* A/B switch (default on; needs sat_free on, circle radius 1..12, gradient offset <= 4): gradientDot, the box sums of
+ * satBlobCenter, circularity and peak classification in ONE kernel that reads the flat image once (no row sums, no SAT) vs
+ * gradient + row prefix sums followed by the streaming circularity kernel; results are bit-identical */
+VP_API int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on);
 /* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
  * tiled kernel; results are bit-identical */
 VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);

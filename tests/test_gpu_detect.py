@@ -74,7 +74,7 @@ def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
     check_frame(got, 0, want)
 
 
-@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat", "sat_free"])
+@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat", "sat_free", "fused_gradcirc"])
 @pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2),
                                 dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, max_blobs=64)])
 def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
@@ -83,7 +83,8 @@ def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
     p, raw, _ = common.make_case(**kw)
     want = port.detect(raw, p)
     setter = getattr(ctx, "set_" + switch)
-    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False), "sat_free": (False, True)}[switch]  # default last
+    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False), "sat_free": (False, True),
+              "fused_gradcirc": (False, True)}[switch]  # default last
     default = values[-1]
     try:
         for value in values:
@@ -106,10 +107,12 @@ def test_sat_fallback_through_every_kernel_variant(ctx, port):
     raw = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
     want = port.detect(raw, p)
     try:
-        for stream_circ, fused_sat, sat_free in [(False, False, True), (True, True, True), (False, True, True), (True, False, False), (True, False, True)]:
+        for stream_circ, fused_sat, sat_free, gc in [(False, False, True, True), (True, True, True, True), (False, True, True, True), (True, False, False, True),
+                                                     (True, False, True, False), (True, False, True, True)]:
             ctx.set_stream_circ(stream_circ)
             ctx.set_fused_sat(fused_sat)
             ctx.set_sat_free(sat_free)
+            ctx.set_fused_gradcirc(gc)
             got = ctx.detect(raw, common.to_vp(p))
             assert got["sat_fallbacks"] == 1
             common.assert_float_images_equal(got["circ"], want["circ"])
@@ -118,6 +121,7 @@ def test_sat_fallback_through_every_kernel_variant(ctx, port):
         ctx.set_stream_circ(True)
         ctx.set_fused_sat(False)
         ctx.set_sat_free(True)
+        ctx.set_fused_gradcirc(True)
 
 
 def test_detect_batch_of_distinct_frames(ctx, port):
@@ -293,8 +297,8 @@ def test_sat_beyond_2p24_falls_back_to_sequential_order(ctx, port):
     check_frame(got, 0, want)
 
 
-@pytest.mark.parametrize("sat_free", [True, False])
-def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free):
+@pytest.mark.parametrize("sat_free,gc", [(True, True), (True, False), (False, False)])
+def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free, gc):
     """Frames that leave the exactness bound -- one through its row sums (wide stripes), one only through the summed-area
     table (found after the fast pass when there is no SAT) -- between clean frames of the same batch: the flagged ones
     are redone in sequential order, the clean ones keep the results of the fast pass."""
@@ -315,6 +319,7 @@ def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free):
     bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
                 m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
     ctx.set_sat_free(sat_free)
+    ctx.set_fused_gradcirc(gc)
     try:
         ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
                                 bufs["m"].device_ptr, bufs["c"].device_ptr)
@@ -324,6 +329,7 @@ def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free):
         m = bufs["m"].read(np.uint8).reshape(n, vp.max_blobs, 22)
     finally:
         ctx.set_sat_free(True)
+        ctx.set_fused_gradcirc(True)
     for i, wt in enumerate(wants):
         common.assert_float_images_equal(circ[i], wt["circ"])
         np.testing.assert_array_equal(counter[i], wt["counter"])

@@ -30,11 +30,13 @@ def full_size_case(sensor_w, sensor_h, k2=0.0, tilt=0.0, fmt=0, n_frames=1, n_ro
     return common.to_vpo(lp), frames
 
 
-@pytest.mark.parametrize("sat_free", [True, False])
+@pytest.mark.parametrize("flow", ["gradcirc", "rowsums", "sat"])
 @pytest.mark.parametrize("radius", list(range(1, 14)))
-def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, sat_free):
-    """circle_radius 1..12 are template instantiations of the streaming circularity kernels, 13 takes the unfused generic
-    path; a lone frame (host API, latency path) and a batch of five distinct frames (device API) each against the oracle."""
+def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
+    """circle_radius 1..12 are template instantiations of the fused gradient + circularity kernel (flow 'gradcirc', the
+    default), of the streaming circularity kernel over row sums ('rowsums') and over a materialised SAT ('sat'); 13 takes
+    the unfused generic path; a lone frame (host API, latency path) and a batch of five distinct frames (device API) each
+    against the oracle."""
     frames = []
     for s_ in range(5):
         p, raw, _ = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=40 + s_,
@@ -45,12 +47,14 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, sat_free)
     wants = [port.detect(f, p) for f in frames]
     assert any(len(w["matches"]) > 0 for w in wants)
     vp = common.to_vp(p)
-    ctx.set_sat_free(sat_free)
+    ctx.set_sat_free(flow != "sat")
+    ctx.set_fused_gradcirc(flow == "gradcirc")
     try:
         got1 = ctx.detect(frames[0], vp)
         got = common.detect_device(ctx, frames, vp)
     finally:
         ctx.set_sat_free(True)
+        ctx.set_fused_gradcirc(True)
     np.testing.assert_array_equal(got1["flat"], wants[0]["flat"])
     np.testing.assert_array_equal(got1["grad"], wants[0]["grad"])
     common.assert_float_images_equal(got1["circ"], wants[0]["circ"])
@@ -58,7 +62,7 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, sat_free)
     common.assert_matches_equal(got1["matches"][0], wants[0]["matches"])
     for i, w in enumerate(wants):
         common.assert_frame_equal(got, i, w)
-    assert (got["plan"]["circ"] == 0) == (radius == 13)
+    assert got["plan"]["circ"] == (0 if radius == 13 else {"gradcirc": 4, "rowsums": 3, "sat": 2}[flow])
 
 
 @pytest.mark.parametrize("offset", [0, 1, 3])

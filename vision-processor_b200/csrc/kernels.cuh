@@ -21,39 +21,10 @@
 #include <type_traits>
 
 #include "vp_b200.h"
+#include "device_util.cuh"
 
 namespace vpk {
 
-constexpr int FMT_RGGB = VP_FMT_RGGB8, FMT_GRBG = VP_FMT_GRBG8, FMT_BGR = VP_FMT_BGR8;
-constexpr int MODE_RTE = VP_SAMPLE_BILINEAR_RTE, MODE_TRUNC = VP_SAMPLE_BILINEAR_TRUNC, MODE_NEAREST = VP_SAMPLE_NEAREST;
-/* Exactness bound of the fast path.  While every row sum and every SAT value stays below 2^22 in magnitude, the
- * fp32 running sums of satHorizontal.cl / satVertical.cl are exact integers AND so is every intermediate of the
- * four 4-tap box sums of satBlobCenter.cl:37-40 (|a-b| < 2^23, |a-b-c| < 2^23+2^22, |a-b-c+d| < 2^24), hence any
- * summation order gives the reference's bits.  Frames that leave the bound are redone in the reference's order. */
-constexpr int SAT_EXACT_LIMIT = 1 << 22;
-
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
-
-/* OpenCL C 6.12.4 min(x, y): "returns y if y < x, otherwise x" -- differs from fminf for (+0, -0) and NaN */
-__device__ __forceinline__ float min_cl(float x, float y) { return y < x ? y : x; }
-
-/* &base[idx] as ONE instruction (IMAD.WIDE.U32): nvcc otherwise expands pointer + 32-bit index into a 4-instruction
- * 64-bit add/shift sequence and rematerialises the base, which matters in kernels that are issue-bound */
-template <class T>
-__device__ __forceinline__ T* elem_ptr(T* base, unsigned idx)
-{
-	static_assert(sizeof(T) == 4, "4-byte elements");
-	unsigned long long r;
-	asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(r) : "r"(idx), "l"(base));
-	return reinterpret_cast<T*>(r);
-}
-
-/* float -> texel index: saturating, NaN -> 0 (fmaxf/fminf return the non-NaN operand) */
-__device__ __forceinline__ int sat_index(float f, int n)
-{
-	f = fminf(fmaxf(f, -1.0f), (float)n);
-	return clampi(__float2int_rz(f), 0, n - 1);
-}
 
 /* ------------------------------------------------------------------------------------------------
  * field -> image projection, kernel/resampling.cl:29-47
@@ -393,42 +364,6 @@ __global__ void __launch_bounds__(256) k_tile_table(const float2* __restrict__ l
 	}
 }
 
-/* Packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2, new on sm_100): two IEEE round-to-nearest operations per issue
- * slot.  The staged kernel is issue-bound, so the two x axes, the two y axes and two samples at a time are evaluated
- * as pairs.  a - b is written fma2(b, -1, a): the product is exact, so the single rounding equals the subtraction's. */
-/* Explicit PTX.  CAUTION: ptxas 12.9 contracts mul.rn.f32x2 followed by add.rn.f32x2 into FFMA2 regardless of -fmad
- * (also through an fma against -0) -- seen in SASS, and in 0.1 % of the pixels as a 1-LSB difference.  A packed product
- * must therefore never feed a packed add: products are packed, their accumulation is scalar (FMUL2 -> FADD is left alone). */
-__device__ __forceinline__ unsigned long long f2_bits(float2 v)
-{
-	unsigned long long r;
-	asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
-	return r;
-}
-__device__ __forceinline__ float2 bits_f2(unsigned long long r)
-{
-	float2 v;
-	asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
-	return v;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b)
-{
-	unsigned long long r;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-	return bits_f2(r);
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b)
-{
-	unsigned long long r;
-	asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
-	return bits_f2(r);
-}
-__device__ __forceinline__ float2 sub2(float2 a, float2 b)
-{
-	unsigned long long r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(b)), "l"(f2_bits(make_float2(-1.0f, -1.0f))), "l"(f2_bits(a)));
-	return bits_f2(r);
-}
 
 /* two tile-relative axes at once (u.x, u.y share the plane dimension): indices into the staged planes, no clamp
  * (edge texels are replicated in the tile); bit-identical to axis_setup */
@@ -593,23 +528,6 @@ constexpr int HNV = TQ_W / 8;              /* 16-byte raw vectors per staged row
 constexpr int HRING = HNV * 2 * TQ_H * 16; /* bytes of one raw stage */
 constexpr size_t HOIST_SMEM = 2 * (size_t)HT * 4 + 2 * (size_t)HRING;
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-/* a + b as ONE packed instruction that ptxas cannot contract with the packed product feeding it: fma(a, 1, b) with a
- * 1.0 the compiler cannot see (a kernel argument).  rn(a*1 + b) == rn(a + b) bit for bit.  With a literal 1.0 -- or a
- * plain add.rn.f32x2 -- ptxas 12.9 folds the preceding mul.rn.f32x2 into an FFMA2 and the product loses its rounding. */
-__device__ __forceinline__ float2 add2_opaque(float2 a, float2 b, unsigned long long one2)
-{
-	unsigned long long r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(one2), "l"(f2_bits(b)));
-	return bits_f2(r);
-}
 
 /* the per-frame arithmetic of one thread's PX pixels (rows ly, ly+RS, ly+2RS, ... of the tile, RS = 16/PX) */
 template <int FMT, bool FULL, int PX>
@@ -666,7 +584,6 @@ __device__ __forceinline__ void hoist_convert(uint4 qq, int edge, float* __restr
 	reinterpret_cast<float4*>(d1)[1] = make_float4(e1[2].x, e1[2].y, e1[3].x, e1[3].y);
 }
 
-template <int V> struct IntC { static constexpr int value = V; };
 
 /* Pipeline of one CTA over its frames 0..n-1 (one barrier per frame, everything addressed statically by frame parity):
  *   raw ring R[0], R[1]  (cp.async; a thread copies and later converts ITS OWN vectors: no cross-thread hand-over)
@@ -1233,18 +1150,6 @@ __global__ void k_gradient_dot(const uint32_t* __restrict__ in, float* __restric
  * row sum leaves the exact range of fp32 (satHorizontal.cl:26-31 would start rounding). */
 /* gradient + exact row prefix sums of one image row by one warp; `srow` may point to global or shared memory.
  * Returns true if a row sum left the exactness bound. */
-/* int -> fp32 for |v| < 2^22 on the integer and FMA pipes (I2F runs on the quarter-rate conversion pipe): adding v to the
- * bit pattern of 1.5 * 2^23 moves the float by v units in the last place, i.e. by exactly v */
-__device__ __forceinline__ float small_int_to_float(int v) { return __fsub_rn(__int_as_float(v + 0x4B400000), 12582912.0f); }
-
-/* `img` is a flat image produced by the reprojection kernels: alpha is 255 in every pixel, so the alpha terms of the four
- * byte dot products cancel (R.U + L.D - R.D - L.U) and need not be masked off as in grad_dot_px */
-__device__ __forceinline__ int grad_dot_opaque(uint32_t R, uint32_t L, uint32_t U, uint32_t D)
-{
-	const uint32_t pos = __dp4a(L, D, __dp4a(R, U, 0u));
-	const uint32_t neg = __dp4a(L, U, __dp4a(R, D, 0u));
-	return (int)pos - (int)neg;
-}
 
 /* (the two helpers below restate the body of row_gradscan for k_grad_rowscan_wide; row_gradscan keeps its own copy because
  * ptxas allocates 8 registers more for it when it is written in terms of them, which costs the batch path occupancy) */
@@ -1656,45 +1561,6 @@ __global__ void __launch_bounds__(256) k_circle(const float* __restrict__ sat, f
 /* ------------------------------------------------------------------------------------------------
  * blob list, blobList.cl:36-102 -- deterministic raster-order compaction
  * ---------------------------------------------------------------------------------------------- */
-struct DiscStats {
-	uint32_t s1[3], s2[3];
-	int n;
-};
-
-__device__ __forceinline__ DiscStats disc_stats(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius)
-{
-	DiscStats d;
-	d.n = 0;
-	d.s1[0] = d.s1[1] = d.s1[2] = d.s2[0] = d.s2[1] = d.s2[2] = 0;
-	const int sq = radius * radius;
-	for (int dy = -radius; dy <= radius; dy++) { /* blobList.cl:63-72 */
-		const uint32_t* row = img + (size_t)clampi(y + dy, 0, h - 1) * w;
-		for (int dx = -radius; dx <= radius; dx++)
-			if (dx * dx + dy * dy <= sq) {
-				const uint32_t v = __ldg(row + clampi(x + dx, 0, w - 1));
-#pragma unroll
-				for (int k = 0; k < 3; k++) {
-					const uint32_t c = (v >> (8 * k)) & 255u;
-					d.s1[k] += c;
-					d.s2[k] += c * c;
-				}
-				d.n++;
-			}
-	}
-	return d;
-}
-
-__device__ __forceinline__ float blob_score(const DiscStats& d, float c)
-{
-	const float fn = (float)d.n;
-	float sd[3];
-#pragma unroll
-	for (int k = 0; k < 3; k++) { /* blobList.cl:76 (native_sqrt -> correctly rounded) */
-		const float f1 = (float)d.s1[k];
-		sd[k] = __fsqrt_rn(__fdiv_rn(__fsub_rn((float)d.s2[k], __fdiv_rn(__fmul_rn(f1, f1), fn)), fn));
-	}
-	return __fdiv_rn(c, __fadd_rn(__fadd_rn(sd[0], sd[1]), sd[2])); /* :78 */
-}
 
 /* classification of one pixel: 0 below threshold, 1 not a local peak, 2 rejected by score, 3 blob */
 struct PeakCtx {
@@ -1742,17 +1608,6 @@ __device__ __forceinline__ void publish_segment(int cls, int lane, int32_t* __re
 	n_peak += __popc(m1);
 }
 
-__device__ __forceinline__ void publish_counters(int lane, int32_t* __restrict__ counter_f, int n_blob, int n_score, int n_peak)
-{
-	if (lane == 0) {
-		if (n_blob)
-			atomicAdd(counter_f + 0, n_blob); /* blobList.cl:87 counts past maxMatches too */
-		if (n_score)
-			atomicAdd(counter_f + 1, n_score); /* :80 */
-		if (n_peak)
-			atomicAdd(counter_f + 2, n_peak); /* :53 */
-	}
-}
 
 /* stage API pass A: a warp = 32 consecutive pixels of a row (x0 multiple of 32) */
 __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h,
@@ -1788,11 +1643,6 @@ __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict_
 constexpr int CT_W = 64, CT_H = 32;
 constexpr int CIRC_PEAKS_MAX_R = 12;
 
-/* blobList.cl:79 for the (non-default) case that the score can reject: kept out of line, it is never hot */
-__device__ __noinline__ int classify_by_score(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, float c, float min_score)
-{
-	return blob_score(disc_stats(img, w, h, x, y, radius), c) < min_score ? 2 : 3;
-}
 
 __device__ __noinline__ float circle_px_generic(const float* __restrict__ sat, int w, int h, int x, int y, int r)
 {
@@ -1966,16 +1816,6 @@ __global__ void __launch_bounds__(256) k_circ_border(const float* __restrict__ s
 	circ_out[fbase + y * w + x] = circle_px(sat + fbase, w, h, x, y, r, (float)(r * r));
 }
 
-/* peak test of one pixel given its circularity and its four (already clamped) neighbours: blobList.cl:38-81 */
-__device__ __forceinline__ int classify_px(const uint32_t* __restrict__ img, int w, int h, int x, int y, int radius, float thr, float min_score,
-                                           int need_score, float cm, float lf, float rt, float up, float dn)
-{
-	if (cm < thr)
-		return 0;
-	if (lf > cm || rt > cm || up > cm || dn > cm)
-		return 1;
-	return need_score ? classify_by_score(img, w, h, x, y, radius, cm, min_score) : 3;
-}
 
 template <int R>
 __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
@@ -2469,7 +2309,7 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
                                                     int max_matches, const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
                                                     const uint32_t* __restrict__ masks, int wpr, uint8_t* __restrict__ matches, size_t match_frame_stride,
                                                     const float* __restrict__ segsum = nullptr, const float* __restrict__ segmax = nullptr, int n_seg = 0,
-                                                    int* __restrict__ flag = nullptr)
+                                                    int* __restrict__ flag = nullptr, GcCheck gc = GcCheck())
 {
 	const int lane = threadIdx.x & 31;
 	const int f = blockIdx.y;
@@ -2481,7 +2321,13 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 		if (threadIdx.x == 0)
 			flag_seen = flag[f];
 		__syncthreads();
-		if (flag_seen == 0 && sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w) && threadIdx.x == 0)
+		if (flag_seen != 0)
+			return;
+		/* fused gradient + circularity flow: ONE more CTA per frame, which evaluates the whole bound from k_grad_circ's side outputs;
+		 * row-sum flow: one CTA per 256 columns over k_circ_stream_rs's column sums of the row sums */
+		const bool bad = gc.striptot ? sat_bound_exceeded_g(gc.segsum, gc.segmax, gc.striptot, gc.scratch, gc.n_seg, gc.seg_rows, w, h, gc.sw, gc.n_strips, f)
+		                             : sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w);
+		if (bad && threadIdx.x == 0)
 			flag[f] = 2;
 		return;
 	}

@@ -6,6 +6,7 @@
  * src/main.cpp:283-289.  Plain CUDA runtime; no torch types, no CPU fallback.
  */
 #include "kernels.cuh"
+#include "gradcirc.h"
 
 #include <algorithm>
 #include <atomic>
@@ -168,7 +169,12 @@ struct vp_ctx {
 	int hoist_chunk = 0;      /* frames per CTA of the hoisted kernel; 0 = automatic */
 	int sm_count = 148;
 	bool stream_circ = true;
+	bool fused_gc = true; /* gradient + circularity + classification in one kernel (gradcirc.cuh); needs sat_free */
+	bool gc_attr = false;
 	bool sat_free = true; /* circularity straight from the row sums: no column scan, no materialised SAT (needs stream_circ, !fused_sat) */
+	int32_t* striptot[MAX_LANES] = {}; /* per lane: k_grad_circ's per-row strip sums of gradDot (frames of the group x strips x rows) */
+	double* gc_scratch[MAX_LANES] = {};
+	size_t striptot_words = 0, gc_scratch_words = 0;
 	float* segsum[MAX_LANES] = {}; /* per lane: column sums of the row sums per (frame of the group, row segment) */
 	float* segmax[MAX_LANES] = {};
 	size_t seg_words = 0;
@@ -476,11 +482,12 @@ size_t raw_frame_bytes(const vp_params* p) { return (size_t)p->wq * p->hq * (siz
 
 int launch_peaks_emit(vp_ctx* ctx, cudaStream_t stream, const uint32_t* flat, const float* circ, int w, int h, int n, int radius, int max_matches,
                       const int32_t* first_slot, const int32_t* rowcount, const uint32_t* masks, uint8_t* matches, size_t match_stride,
-                      const float* segsum = nullptr, const float* segmax = nullptr, int n_seg = 0, int* flag = nullptr)
+                      const float* segsum = nullptr, const float* segmax = nullptr, int n_seg = 0, int* flag = nullptr, GcCheck gc = GcCheck())
 {
-	/* segsum given: ceil(w/256) more CTAs per frame check the exactness bound of the SAT (see k_peaks_emit) */
-	k_peaks_emit<<<dim3(cdiv(h, 8) + (segsum ? cdiv(w, 256) : 0), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks, cdiv(w, 32),
-	                                                                          matches, match_stride, segsum, segmax, n_seg, flag);
+	/* segsum given: more CTAs per frame check the exactness bound of the SAT next to the record warps (see k_peaks_emit):
+	 * one per 256 columns for the row-sum flow, ONE for the fused gradient + circularity kernel */
+	k_peaks_emit<<<dim3(cdiv(h, 8) + (segsum ? (gc.striptot ? 1 : cdiv(w, 256)) : 0), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks,
+	                                                                                          cdiv(w, 32), matches, match_stride, segsum, segmax, n_seg, flag, gc);
 	return check_launch(ctx, "k_peaks_emit");
 }
 
@@ -563,15 +570,33 @@ __global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict_
 	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
 }
 
+/* flow of the fused gradient + circularity kernel: the bound has been evaluated (k_sat_check_g / k_peaks_emit); a flagged frame
+ * forgets what the fast pass published and gets its SAT in the reference's sequential order for k_circ_stream's literal path */
+__global__ void __launch_bounds__(1024) k_sat_fix_clear(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
+                                                        const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                                                        uint32_t* __restrict__ masks, int wpr)
+{
+	const int f = blockIdx.x;
+	if (flag[f] == 0)
+		return;
+	for (int i = threadIdx.x; i < h * wpr; i += 1024)
+		masks[(size_t)f * h * wpr + i] = 0u;
+	for (int i = threadIdx.x; i < h; i += 1024)
+		rowcount[(size_t)f * h + i] = 0;
+	if (threadIdx.x < 3)
+		counter[3 * f + threadIdx.x] = 0;
+	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
+}
+
 /* rows per CTA of the streaming circularity kernels: 128 (few halo rows per segment) whenever that already gives the GPU two
  * CTAs per SM; fewer frames or smaller images take 64 or 32 rows and trade halo work for shorter dependent chains and a
  * full GPU (a lone 1224x1024 frame has only 14 x 8 CTAs to offer at 128 rows) */
-int circ_seg_rows(const vp_ctx* ctx, int wf, int hf, int n_frames, int r)
+int circ_seg_rows(const vp_ctx* ctx, int wf, int hf, int n_frames, int r, bool gc)
 {
 	static const int seg_env = getenv("VP_CIRC_SEG") ? atoi(getenv("VP_CIRC_SEG")) : 0; /* tuning aid */
 	if (seg_env > 0)
 		return seg_env;
-	const int swu = 32 - (r + 2) - 1; /* output columns per warp, see k_circ_stream_rs */
+	const int swu = gc ? grad_circ_strip_width(r) : 32 - (r + 2) - 1; /* output columns per warp, see k_grad_circ / k_circ_stream_rs */
 	const long long per_row_of_segments = (long long)cdiv(cdiv(wf, swu > 0 ? swu : 1), 4) * n_frames;
 	for (int seg = 128; seg > 32; seg >>= 1)
 		if (per_row_of_segments * cdiv(hf, seg) >= 2LL * ctx->sm_count)
@@ -721,6 +746,8 @@ void vp_ctx_destroy(vp_ctx* c)
 		cudaFree(c->sat[l]);
 		cudaFree(c->segsum[l]);
 		cudaFree(c->segmax[l]);
+		cudaFree(c->striptot[l]);
+		cudaFree(c->gc_scratch[l]);
 		if (l > 0 && c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
 		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
 	}
@@ -780,6 +807,13 @@ int vp_ctx_set_sat_free(vp_ctx* ctx, int on) /* A/B switch: circularity from the
 {
 	REQUIRE(ctx, ctx, "ctx is null");
 	ctx->sat_free = on != 0;
+	return VP_OK;
+}
+
+int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on) /* A/B switch: one gradient + circularity kernel vs row sums + streaming circularity */
+{
+	REQUIRE(ctx, ctx, "ctx is null");
+	ctx->fused_gc = on != 0;
 	return VP_OK;
 }
 
@@ -1413,9 +1447,14 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
 	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
-	const int seg = circ_seg_rows(ctx, wf, hf, n_frames, p->circle_radius);
-	const int n_seg = cdiv(hf, seg);
 	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
+	const bool use_gc = sat_free && ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
+	const int seg = circ_seg_rows(ctx, wf, hf, n_frames, p->circle_radius, use_gc);
+	const int n_seg = cdiv(hf, seg);
+	if (use_gc && !ctx->gc_attr) {
+		CK(ctx, (cudaError_t)grad_circ_prepare());
+		ctx->gc_attr = true;
+	}
 	if (sat_free) {
 		const size_t need = (size_t)G * n_seg * wf;
 		if (need > ctx->seg_words) {
@@ -1431,6 +1470,27 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 				CK(ctx, cudaMalloc(&ctx->segmax[l], need * 4));
 			}
 			ctx->seg_words = need;
+		}
+	}
+	const int gc_strips = use_gc ? grad_circ_strips(p->circle_radius, wf) : 0;
+	if (use_gc) {
+		const size_t need_t = (size_t)G * gc_strips * hf, need_s = (size_t)G * 2 * gc_strips * n_seg;
+		if (need_t > ctx->striptot_words || need_s > ctx->gc_scratch_words) {
+			CK(ctx, cudaDeviceSynchronize());
+			const size_t nt = std::max(need_t, ctx->striptot_words), nsc = std::max(need_s, ctx->gc_scratch_words);
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+				cudaFree(ctx->striptot[l]);
+				cudaFree(ctx->gc_scratch[l]);
+				ctx->striptot[l] = nullptr;
+				ctx->gc_scratch[l] = nullptr;
+			}
+			ctx->striptot_words = ctx->gc_scratch_words = 0;
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
+				CK(ctx, cudaMalloc(&ctx->striptot[l], nt * 4));
+				CK(ctx, cudaMalloc(&ctx->gc_scratch[l], nsc * 8));
+			}
+			ctx->striptot_words = nt;
+			ctx->gc_scratch_words = nsc;
 		}
 	}
 	/* single-pass gradient + SAT: a strip of srows rows x full width lives in shared memory */
@@ -1482,7 +1542,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	plan_out[1] = 1;
 	plan_out[2] = G;
 	plan_out[3] = lanes;
-	plan_out[4] = sat_free ? 3 : fused_circ ? (ctx->stream_circ ? 2 : 1) : 0;
+	plan_out[4] = use_gc ? 4 : sat_free ? 3 : fused_circ ? (ctx->stream_circ ? 2 : 1) : 0;
 	plan_out[5] = seg;
 	plan_out[6] = plan_out[7] = 0;
 
@@ -1627,7 +1687,12 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			}
 			if (rc) return rc;
 		}
-		if (sat_free) {
+		if (use_gc) {
+			/* gradientDot + windows + circularity + classification in one pass over the flat image (gradcirc.cuh) */
+			Stage st(ctx, "grad_circ", 1, s);
+			CK(ctx, (cudaError_t)launch_grad_circ(s, p->circle_radius, flat, grad, circ, wf, hf, p->grad_offset, seg, g, p->circ_threshold, p->min_score,
+			                                      p->blob_radius, ns, counter, rowcount, masks, wpr, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane]));
+		} else if (sat_free) {
 			Stage st(ctx, "grad_rowscan", 1, s);
 			static const int wide_env = getenv("VP_GRAD_WIDE") ? atoi(getenv("VP_GRAD_WIDE")) : -1; /* tuning aid / A-B */
 			const bool wide = (wide_env >= 0 ? wide_env != 0 : g <= 2) && cdiv(wf, 128) <= ROWWIDE_MAX_WARPS;
@@ -1663,7 +1728,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			const int r = p->circle_radius;
 			float* segsum = ctx->segsum[lane];
 			float* segmax = ctx->segmax[lane];
-			{
+			if (!use_gc) {
 				Stage st(ctx, "circ_peaks", 1, s);
 #define VP_CSR(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
@@ -1681,15 +1746,21 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			if (!defer_fallback) {
 				/* the exactness bound of the summed-area table, checked after the fact; frames that left it (or whose row sums
 				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
-				Stage st(ctx, "sat_check", 2, s);
-				k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
+				Stage st(ctx, "sat_check", use_gc ? 3 : 2, s);
+				if (use_gc) {
+					CK(ctx, (cudaError_t)launch_sat_check_g(s, r, segsum, segmax, ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf, g, flag));
+					k_sat_fix_clear<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
+				} else {
+					k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
+				}
 #define VP_CSF(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, fb_seg), g);                                                          \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, fb_seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
 		                                       rowcount, masks, wpr, 1);                                                       \
 	} break;
+				const int fb_seg = 128; /* the fallback pass picks its own segments: nothing is handed over by rows */
 				switch (r) {
 					VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
 				}
@@ -1739,10 +1810,22 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 		}
 		{
 			Stage st(ctx, "peaks_emit", 1, s);
-			if (defer_fallback)
+			if (defer_fallback) {
+				GcCheck gc;
+				if (use_gc) {
+					gc.segsum = ctx->segsum[lane];
+					gc.segmax = ctx->segmax[lane];
+					gc.striptot = ctx->striptot[lane];
+					gc.scratch = ctx->gc_scratch[lane];
+					gc.n_seg = n_seg;
+					gc.seg_rows = seg;
+					gc.sw = grad_circ_strip_width(p->circle_radius);
+					gc.n_strips = gc_strips;
+				}
 				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
 				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22, ctx->segsum[lane], ctx->segmax[lane], n_seg,
-				                       flag);
+				                       flag, gc);
+			}
 			else
 				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
 				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22);
@@ -1767,20 +1850,24 @@ static int redo_flagged(vp_ctx* ctx, int n_frames, const vp_params* p, uint8_t* 
                         int32_t* d_counter, int* flags)
 {
 	const int wf = p->wf, hf = p->hf, wpr = cdiv(wf, 32);
-	const int r = p->circle_radius, seg = circ_seg_rows(ctx, wf, hf, n_frames, r), n_seg = cdiv(hf, seg);
+	const bool use_gc = ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
+	const int r = p->circle_radius, seg = circ_seg_rows(ctx, wf, hf, n_frames, r, use_gc), n_seg = cdiv(hf, seg);
 	const int ns = need_score(p->circ_threshold, p->min_score);
 	cudaStream_t s = ctx->stream;
 	uint32_t* flat = (uint32_t*)d_flat;
 	float* sat = ctx->sat[0];
 	int rc;
 	Stage st(ctx, "sat_check", 3, s);
-	k_sat_check_fix<<<n_frames, 1024, 0, s>>>(ctx->segsum[0], ctx->segmax[0], n_seg, d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount,
-	                                          ctx->masks, wpr);
+	if (use_gc) /* the flags are final: the bound was evaluated next to the record kernel */
+		k_sat_fix_clear<<<n_frames, 1024, 0, s>>>(d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount, ctx->masks, wpr);
+	else
+		k_sat_check_fix<<<n_frames, 1024, 0, s>>>(ctx->segsum[0], ctx->segmax[0], n_seg, d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount,
+		                                          ctx->masks, wpr);
 #define VP_CSF(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, n_frames);                                                              \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, 128), n_frames);                                                      \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, 128, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
 		                                       ctx->rowcount, ctx->masks, wpr, 1);                                             \
 	} break;
 	switch (r) {
@@ -1982,10 +2069,10 @@ static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p,
 		}
 	}
 	const void* ptrs[18] = { s.raw, s.flat, s.grad, s.circ, s.results, s.results_host, ctx->rowsum[0], ctx->sat[0], ctx->segsum[0], ctx->segmax[0],
-		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->sync_words, ctx->agg[0] };
+		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->striptot[0], ctx->gc_scratch[0] };
 	memcpy(fp->ptr, ptrs, sizeof ptrs);
 	const int knobs[10] = { ctx->staged_reproject, ctx->sat_free, ctx->stream_circ, ctx->fused_sat, ctx->hoist_chunk, ctx->group, ctx->lanes, ctx->strips,
-		                    ctx->profiling, 0 };
+		                    ctx->profiling, ctx->fused_gc };
 	memcpy(fp->knob, knobs, sizeof knobs);
 }
 

@@ -160,6 +160,7 @@ def load() -> C.CDLL:
         "vp_ctx_set_sat_free": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
+        "vp_ctx_set_fused_gradcirc": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
         "vp_detect_last_plan": (C.c_int, [vp, C.POINTER(C.c_int32)]),
@@ -449,6 +450,10 @@ class Context:
 
     def set_stream_circ(self, on: bool):
         self._ck(self.lib.vp_ctx_set_stream_circ(self.h, int(on)))
+
+    def set_fused_gradcirc(self, on: bool):
+        """One gradient + circularity kernel (default) vs gradient + row sums followed by the streaming circularity kernel."""
+        self._ck(self.lib.vp_ctx_set_fused_gradcirc(self.h, int(on)))
 
     def set_fused_sat(self, on: bool):
         self._ck(self.lib.vp_ctx_set_fused_sat(self.h, int(on)))
