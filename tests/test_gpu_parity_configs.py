@@ -62,7 +62,8 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
     common.assert_matches_equal(got1["matches"][0], wants[0]["matches"])
     for i, w in enumerate(wants):
         common.assert_frame_equal(got, i, w)
-    assert got["plan"]["circ"] == (0 if radius == 13 else {"gradcirc": 4, "rowsums": 3, "sat": 2}[flow])
+    gc_fits = p.grad_offset <= 4 and 2 * p.grad_offset <= radius + 2  # else the fused kernel hands over to the row-sum flow
+    assert got["plan"]["circ"] == (0 if radius == 13 else {"gradcirc": 4 if gc_fits else 3, "rowsums": 3, "sat": 2}[flow])
 
 
 @pytest.mark.parametrize("offset", [0, 1, 3])

@@ -27,12 +27,15 @@ ap.add_argument("--reproject", type=int, default=2, help="0 direct gather, 1 sta
 ap.add_argument("--chunk", type=int, default=0, help="frames per CTA of the hoisted reprojection (0 = automatic)")
 ap.add_argument("--tiled-circ", action="store_true", help="shared-memory tiled circularity kernel instead of the streaming one")
 ap.add_argument("--fused-sat", action="store_true", help="single-pass gradient+SAT kernel instead of row scan + column scan")
+ap.add_argument("--width", type=int, default=2448)
+ap.add_argument("--height", type=int, default=2048)
+ap.add_argument("--no-gradcirc", action="store_true", help="row sums + streaming circularity instead of the fused gradient + circularity kernel")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--times", action="store_true", help="print CUDA-event time per step and per stage")
 args = ap.parse_args()
 
-lp, frames = bench.build_workload(4)
+lp, frames = bench.build_workload(args.width, args.height, 4)
 p = lib.params_from_launch(lp)
 B, nf, rb = args.batch, lp.wf * lp.hf, frames.shape[1]
 dev = torch.device("cuda", 0)
@@ -52,6 +55,7 @@ ctx.set_staged_reproject(0 if args.direct else args.reproject)
 ctx.set_hoist_chunk(args.chunk)
 ctx.set_stream_circ(not args.tiled_circ)
 ctx.set_fused_sat(args.fused_sat)
+ctx.set_fused_gradcirc(not args.no_gradcirc)
 
 
 def step():

@@ -86,6 +86,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 {
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -186,96 +190,86 @@ __device__ __forceinline__ int classify_px(const uint32_t* __restrict__ img, int
 
 /* side outputs of k_grad_circ and what sat_bound_exceeded_g needs to read them (by value to the kernels that check the bound) */
 struct GcCheck {
-	float* segsum = nullptr;
+	const float* segsum = nullptr;
 	const float* segmax = nullptr;
-	int32_t* striptot = nullptr; /* nullptr: not the fused gradient + circularity flow */
-	double* scratch = nullptr;
+	const int32_t* striptot = nullptr; /* nullptr: not the fused gradient + circularity flow */
+	float* scratch = nullptr;          /* gc_check_scratch_words() 4-byte words per frame */
 	int n_seg = 0, seg_rows = 0, sw = 0, n_strips = 0;
 };
+__host__ __device__ inline size_t gc_check_scratch_words(int n_strips, int n_seg, int w) { return (size_t)2 * n_strips * n_seg + (size_t)n_seg * w; }
 
 /* The exactness bound of the reference's summed-area table for one frame from what k_grad_circ leaves behind:
  *   S(c, k), A(c, k)   per column c and row segment k: the column sum of gradDot over the segment and the largest magnitude
  *                      the running sum reached on the way (segsum, segmax: n_seg x w floats per frame),
- *   T(s, y)            per strip s (the `sw` output columns of one warp) and row y: the sum of gradDot over the strip's
- *                      columns (striptot: n_strips x h int32 per frame).
+ *   P(s, y)            per strip s (the `sw` output columns of one warp) and row y: the sum of gradDot over the strip's columns
+ *                      and the rows of y's segment up to y (striptot: n_strips x h int32 per frame; exact).
  * For a pixel (x, y) in strip s and segment k:
- *   SAT(x, y) = [sum over the strips left of s and the rows <= y of T]                        exact, from T alone
- *             + sum_{c in s, c <= x} [carry(c, k) + running column sum inside segment k]       carry(c, k) = sum_{k' < k} S(c, k')
- *   |SAT(x, y)| <= max_{y in k} |left(s, y)| + max_{x in s} |prefix of the carries| + sum_{c in s} A(c, k).
- * Called by a whole CTA; works IN PLACE (T becomes its prefix over strips, S the carries), so once per frame; `scratch`
- * holds 2 * n_strips * n_seg doubles per frame.  Every thread returns the same answer: true when some |SAT| -- and with
+ *   SAT(x, y) = sum_{s' < s} [carry(s', k) + P(s', y)]                                      exact: the strips to the left
+ *             + sum_{c in s, c <= x} [carry(c, k) + running column sum inside segment k]      carry(., k) = the sums of the segments above
+ *   |SAT(x, y)| <= max_{y in k} |left(s, y)| + max_{x in s} |prefix of the column carries| + sum_{c in s} A(c, k).
+ * Called by a whole CTA (a multiple of 32 threads); every thread returns the same answer: true when some |SAT| -- and with
  * it possibly a row prefix sum, |RS| <= 2 max |SAT| -- may have reached SAT_EXACT_LIMIT.  About twice the true maximum on
- * camera-like frames. */
-__device__ __forceinline__ bool sat_bound_exceeded_g(float* __restrict__ segsum, const float* __restrict__ segmax, int32_t* __restrict__ striptot,
-                                                     double* __restrict__ scratch, int n_seg, int seg_rows, int w, int h, int sw, int n_strips, int f)
+ * camera-like frames.  fp32 throughout: integer values are exact below 2^24, and any term that is not is four times
+ * the limit already. */
+__device__ __forceinline__ bool sat_bound_exceeded_g(const GcCheck& gc, int w, int h, int f)
 {
-	const int tid = threadIdx.x, nt = blockDim.x;
-	int32_t* M = striptot + (size_t)f * n_strips * h;
-	float* S = segsum + (size_t)f * n_seg * w;
-	const float* A = segmax + (size_t)f * n_seg * w;
-	double* segtot = scratch + (size_t)f * 2 * n_strips * n_seg; /* [s][k] */
-	double* leftmax = segtot + (size_t)n_strips * n_seg;
+	const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+	const int n_seg = gc.n_seg, seg_rows = gc.seg_rows, n_strips = gc.n_strips;
+	const int32_t* __restrict__ P = gc.striptot + (size_t)f * n_strips * h;
+	const float* __restrict__ S = gc.segsum + (size_t)f * n_seg * w;
+	const float* __restrict__ A = gc.segmax + (size_t)f * n_seg * w;
+	float* __restrict__ strip_carry = gc.scratch + (size_t)f * gc_check_scratch_words(n_strips, n_seg, w); /* [s][k] */
+	unsigned* __restrict__ left_max = reinterpret_cast<unsigned*>(strip_carry + (size_t)n_strips * n_seg); /* [s][k], bits of a non-negative float */
+	float* __restrict__ col_carry = strip_carry + (size_t)2 * n_strips * n_seg;                             /* [k][x] */
 	const int n_pairs = n_strips * n_seg;
-	/* T -> prefix over strips (|row sum| <= w * 195075 < 2^31 for w <= 11000) */
-	for (int y = tid; y < h; y += nt) {
-		int acc = 0;
-		for (int s = 0; s < n_strips; s++) {
-			acc += M[(size_t)s * h + y];
-			M[(size_t)s * h + y] = acc;
-		}
-	}
-	/* S -> carries (exclusive prefix over the segments); fp32 sums of integers: exact below 2^24, and anything that large is
-	 * far beyond the limit anyway */
-	for (int x = tid; x < w; x += nt) {
+	for (int s = tid; s < n_strips; s += nt) { /* what the segments above segment k add to strip s */
 		float c = 0.0f;
 		for (int k = 0; k < n_seg; k++) {
-			const float v = S[(size_t)k * w + x];
-			S[(size_t)k * w + x] = c;
-			c += v;
+			strip_carry[s * n_seg + k] = c;
+			left_max[s * n_seg + k] = 0u;
+			c += (float)P[(size_t)s * h + (min((k + 1) * seg_rows, h) - 1)];
 		}
 	}
-	__syncthreads();
-	for (int p = tid; p < n_pairs; p += nt) { /* sum of the strip-prefixed row sums over segment k */
-		const int s = p / n_seg, k = p - s * n_seg;
-		const int y0 = k * seg_rows, y1 = min(y0 + seg_rows, h);
-		double t = 0.0;
-		for (int y = y0; y < y1; y++)
-			t += (double)M[(size_t)s * h + y];
-		segtot[p] = t;
-	}
-	__syncthreads();
-	for (int s = tid; s < n_strips; s += nt) { /* exclusive prefix over the segments */
-		double c = 0.0;
+	for (int x = tid; x < w; x += nt) { /* ... and to column x */
+		float c = 0.0f;
+#pragma unroll 4
 		for (int k = 0; k < n_seg; k++) {
-			const double v = segtot[s * n_seg + k];
-			segtot[s * n_seg + k] = c;
-			c += v;
+			col_carry[(size_t)k * w + x] = c;
+			c += S[(size_t)k * w + x];
 		}
 	}
 	__syncthreads();
-	for (int p = tid; p < n_pairs; p += nt) { /* largest |SAT| along the right edge of strip s inside segment k */
-		const int s = p / n_seg, k = p - s * n_seg;
-		const int y0 = k * seg_rows, y1 = min(y0 + seg_rows, h);
-		double acc = segtot[p], mx = 0.0;
-		for (int y = y0; y < y1; y++) {
-			acc += (double)M[(size_t)s * h + y];
-			mx = fmax(mx, fabs(acc));
+	/* the summed-area table along the right edge of every strip, row by row: one thread per row walks the strips */
+	const bool warp_rows_share_segment = (seg_rows & 31) == 0;
+	for (int y0 = 0; y0 < h; y0 += nt) {
+		const int y = y0 + tid;
+		const int k = min(y, h - 1) / seg_rows;
+		float acc = 0.0f;
+		for (int s = 0; s + 1 < n_strips; s++) {
+			if (y < h)
+				acc += strip_carry[s * n_seg + k] + (float)P[(size_t)s * h + y];
+			const unsigned mine = y < h ? __float_as_uint(fabsf(acc)) : 0u;
+			if (warp_rows_share_segment) { /* y0 and nt are multiples of 32: the 32 rows of a warp lie in one segment */
+				const unsigned m = __reduce_max_sync(0xffffffffu, mine);
+				if (lane == 0 && m)
+					atomicMax(left_max + (s + 1) * n_seg + k, m);
+			} else if (mine) {
+				atomicMax(left_max + (s + 1) * n_seg + k, mine);
+			}
 		}
-		leftmax[p] = mx;
 	}
 	__syncthreads();
 	bool bad = false;
 	for (int p = tid; p < n_pairs; p += nt) {
 		const int s = p / n_seg, k = p - s * n_seg;
-		const int x0 = s * sw, x1 = min(x0 + sw, w);
-		double pre = 0.0, in_pre = 0.0, in_a = 0.0;
+		const int x0 = s * gc.sw, x1 = min(x0 + gc.sw, w);
+		float pre = 0.0f, in_pre = 0.0f, in_a = 0.0f;
 		for (int x = x0; x < x1; x++) {
-			pre += (double)S[(size_t)k * w + x];
-			in_pre = fmax(in_pre, fabs(pre));
-			in_a += (double)A[(size_t)k * w + x];
+			pre += col_carry[(size_t)k * w + x];
+			in_pre = fmaxf(in_pre, fabsf(pre));
+			in_a += A[(size_t)k * w + x];
 		}
-		const double left = s > 0 ? leftmax[p - n_seg] : 0.0;
-		bad |= !(left + in_pre + in_a < (double)SAT_EXACT_LIMIT);
+		bad |= !(__uint_as_float(left_max[p]) + in_pre + in_a < (float)SAT_EXACT_LIMIT);
 	}
 	return __syncthreads_or(bad);
 }

@@ -5,16 +5,13 @@
 namespace vpk {
 
 /* batch path: one CTA per frame evaluates the bound and raises the frame's flag */
-__global__ void __launch_bounds__(1024) k_sat_check_g(float* __restrict__ segsum, const float* __restrict__ segmax, int32_t* __restrict__ striptot,
-                                                      double* __restrict__ scratch, int n_seg, int seg_rows, int w, int h, int sw, int n_strips,
-                                                      int* __restrict__ flag)
+__global__ void __launch_bounds__(1024) k_sat_check_g(GcCheck gc, int w, int h, int* __restrict__ flag)
 {
 	const int f = blockIdx.x;
-	if (sat_bound_exceeded_g(segsum, segmax, striptot, scratch, n_seg, seg_rows, w, h, sw, n_strips, f) && threadIdx.x == 0)
+	if (sat_bound_exceeded_g(gc, w, h, f) && threadIdx.x == 0)
 		flag[f] = 2;
 }
 
-/* 2*o <= D: the rows a group reads and the next group's rows in flight fit the three ring slots */
 bool grad_circ_supported(int r, int o) { return r >= 1 && r <= GC_MAX_R && o >= 0 && o <= GC_MAX_OFFSET && 2 * o <= r + 2; }
 
 int grad_circ_strip_width(int r) { return gc_strip_width(r); }
@@ -60,11 +57,23 @@ int launch_grad_circ(cudaStream_t stream, int r, const uint32_t* flat, float* gr
 
 int grad_circ_strips(int r, int w) { return (w + gc_strip_width(r) - 1) / gc_strip_width(r); }
 
-int launch_sat_check_g(cudaStream_t stream, int r, float* segsum, const float* segmax, int32_t* striptot, double* scratch, int seg_rows, int w, int h,
-                       int n_frames, int* flag)
+GcCheck grad_circ_check(int r, const float* segsum, const float* segmax, const int32_t* striptot, float* scratch, int seg_rows, int w, int h)
 {
-	const int n_seg = (h + seg_rows - 1) / seg_rows;
-	k_sat_check_g<<<n_frames, 1024, 0, stream>>>(segsum, segmax, striptot, scratch, n_seg, seg_rows, w, h, gc_strip_width(r), grad_circ_strips(r, w), flag);
+	GcCheck gc;
+	gc.segsum = segsum;
+	gc.segmax = segmax;
+	gc.striptot = striptot;
+	gc.scratch = scratch;
+	gc.seg_rows = seg_rows;
+	gc.n_seg = (h + seg_rows - 1) / seg_rows;
+	gc.sw = gc_strip_width(r);
+	gc.n_strips = grad_circ_strips(r, w);
+	return gc;
+}
+
+int launch_sat_check_g(cudaStream_t stream, const GcCheck& gc, int w, int h, int n_frames, int* flag)
+{
+	k_sat_check_g<<<n_frames, 1024, 0, stream>>>(gc, w, h, flag);
 	return (int)cudaGetLastError();
 }
 

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	const bool cols_free = xs - HL >= 1 && xs - HL + 63 <= w - 1;
 	const bool ea = c0 >= 1 && c0 <= w - 1, eb = c0 + 1 >= 1 && c0 + 1 <= w - 1;
 	const uint32_t my = smem_u32(ring) + (uint32_t)(2 * lane + GC_OH) * 4u; /* shared address of column c0 in slot 0 */
+	const int ecol[3] = { clampi(xl + lane, 0, w - 1), clampi(xl + lane + 32, 0, w - 1), clampi(xl + lane + 64, 0, w - 1) }; /* edge strips: CLAMP_TO_EDGE in x */
 	int nb = 0, ns = 0, npk = 0;
 	int32_t* rcf = rowcount + f * h;
 	uint32_t* mkf = masks + (size_t)f * h * wpr;
@@ -239,20 +240,25 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 					bulk_copy_g2s(ring + (p + mirror) * GC_ROWBYTES, src, GC_ROWBYTES, bars + stage);
 			}
 		} else {
+			/* strips at the image edge (or rows that are not 16-byte aligned): 4-byte cp.async with clamped columns, three staged
+			 * words per lane and row; asynchronous like the bulk copies, completion through cp.async groups */
 			for (int i = 0; i < n; i++) {
 				const int pi = __shfl_sync(0xffffffffu, p, i), mi = __shfl_sync(0xffffffffu, mirror, i);
 				const uint32_t* src = flatf + (size_t)clampi(first + i, 0, h - 1) * w;
-				uint32_t* dst = reinterpret_cast<uint32_t*>(ring + pi * GC_ROWBYTES);
-				for (int j = lane; j < GC_NW; j += 32) {
-					const uint32_t v = __ldg(src + clampi(xl + j, 0, w - 1));
-					dst[j] = v;
-					if (mi)
-						dst[mi * GC_NW + j] = v;
+				unsigned char* dst = ring + pi * GC_ROWBYTES + lane * 4;
+#pragma unroll
+				for (int q = 0; q < 3; q++) {
+					if (q < 2 || lane < GC_NW - 64) {
+						cp_async4(dst + q * 128, src + ecol[q]);
+						if (mi)
+							cp_async4(dst + mi * GC_ROWBYTES + q * 128, src + ecol[q]);
+					}
 				}
 			}
-			__syncwarp();
+			cp_async_commit();
 		}
 	};
+	(void)stage_rows;
 
 	float2 gq[D], hold[K > 0 ? K : 1], qa[D];
 #pragma unroll
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	float2 c_prev2 = make_float2(0.f, 0.f), c_prev1 = make_float2(0.f, 0.f); /* the last two circularity rows of the previous group */
 	float2 V = make_float2(0.f, 0.f);
 	float2 colrun = make_float2(0.f, 0.f), colmax = make_float2(0.f, 0.f);
+	int strip_run = 0; /* sum of gradDot over the strip's own columns and the segment's rows so far (warp-uniform, exact) */
 	const int t0 = ys - 1 - R;
 	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
 	/* output pointers of this lane's column pair, advanced row by row: gradDot row tau and circularity row y = tau - R */
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		float2 crow[D + 2];   /* circularity rows y0-2 .. y0+D-1 */
 		crow[0] = c_prev2;
 		crow[1] = c_prev1;
-		int strip_row = 0; /* lane s: the sum of gradDot over the strip's own columns in row t+s */
+		int strip_row = 0; /* lane s: the strip's running sum after row t+s */
 #pragma unroll
 		for (int s = 0; s < D; s++) {
 			const int tau = t + s;
@@ -304,10 +311,10 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 			if (out_lane && own_row)
 				*reinterpret_cast<float2*>(pg) = gf;
 			pg = bump(pg, w4);
-			{ /* what the exactness bound of the SAT is made of: per row the strip's sum (exact, one warp reduction) ... */
-				const int rt = __reduce_add_sync(0xffffffffu, out_lane ? g0 + g1 : 0);
+			if (own_row) { /* what the exactness bound of the SAT is made of: the strip's running sum after every row (one warp reduction) ... */
+				strip_run += __reduce_add_sync(0xffffffffu, out_lane ? g0 + g1 : 0);
 				if (lane == s)
-					strip_row = rt;
+					strip_row = strip_run;
 			}
 			if (own_row) { /* ... and per column the sum over the segment's rows */
 				colrun = add2(colrun, gf);
@@ -387,8 +394,12 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 #pragma unroll 1
 	for (int g = 0; g < n_groups; g++) {
 		const int t = t0 + g * D;
-		if (bulk)
+		if (bulk) {
 			mbar_wait(bars + (g & 1), (uint32_t)(g >> 1) & 1u);
+		} else {
+			cp_async_wait<0>(); /* this group's rows (the next group's are issued below) */
+			__syncwarp();
+		}
 		const int next = slot == 2 ? 0 : slot + 1;
 		if (g + 1 < n_groups) /* the D rows the next group adds: its relative rows o .. D-1+o */
 			stage_rows(t + D + o, D, next * D + o, (g + 1) & 1);

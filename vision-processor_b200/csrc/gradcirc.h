@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "device_util.cuh"
+
 namespace vpk {
 
 /* can k_grad_circ run this configuration?  (radius 1..12, gradient offset <= 4; anything else takes the row-sum kernels) */
@@ -20,9 +22,9 @@ int grad_circ_strips(int circle_radius, int w);
 int launch_grad_circ(cudaStream_t stream, int circle_radius, const uint32_t* flat, float* grad, float* circ, int w, int h, int grad_offset, int seg_rows,
                      int n_frames, float thr, float min_score, int blob_radius, int need_score, int32_t* counter, int32_t* rowcount, uint32_t* masks, int wpr,
                      float* segsum, float* segmax, int32_t* striptot);
-/* the bound itself (one CTA per frame, works in place on the side outputs; scratch: n_frames x 2 x strips x n_seg doubles):
- * raises flag[f] = 2 for frames that may have left it */
-int launch_sat_check_g(cudaStream_t stream, int circle_radius, float* segsum, const float* segmax, int32_t* striptot, double* scratch, int seg_rows, int w,
-                       int h, int n_frames, int* flag);
+/* what the bound check reads (device_util.cuh: GcCheck); scratch: gc_check_scratch_words() 4-byte words per frame */
+GcCheck grad_circ_check(int circle_radius, const float* segsum, const float* segmax, const int32_t* striptot, float* scratch, int seg_rows, int w, int h);
+/* the bound itself, one CTA per frame: raises flag[f] = 2 for frames that may have left it */
+int launch_sat_check_g(cudaStream_t stream, const GcCheck& gc, int w, int h, int n_frames, int* flag);
 
 } // namespace vpk

@@ -2325,7 +2325,7 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 			return;
 		/* fused gradient + circularity flow: ONE more CTA per frame, which evaluates the whole bound from k_grad_circ's side outputs;
 		 * row-sum flow: one CTA per 256 columns over k_circ_stream_rs's column sums of the row sums */
-		const bool bad = gc.striptot ? sat_bound_exceeded_g(gc.segsum, gc.segmax, gc.striptot, gc.scratch, gc.n_seg, gc.seg_rows, w, h, gc.sw, gc.n_strips, f)
+		const bool bad = gc.striptot ? sat_bound_exceeded_g(gc, w, h, f)
 		                             : sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w);
 		if (bad && threadIdx.x == 0)
 			flag[f] = 2;

@@ -173,7 +173,7 @@ struct vp_ctx {
 	bool gc_attr = false;
 	bool sat_free = true; /* circularity straight from the row sums: no column scan, no materialised SAT (needs stream_circ, !fused_sat) */
 	int32_t* striptot[MAX_LANES] = {}; /* per lane: k_grad_circ's per-row strip sums of gradDot (frames of the group x strips x rows) */
-	double* gc_scratch[MAX_LANES] = {};
+	float* gc_scratch[MAX_LANES] = {};
 	size_t striptot_words = 0, gc_scratch_words = 0;
 	float* segsum[MAX_LANES] = {}; /* per lane: column sums of the row sums per (frame of the group, row segment) */
 	float* segmax[MAX_LANES] = {};
@@ -1474,7 +1474,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	}
 	const int gc_strips = use_gc ? grad_circ_strips(p->circle_radius, wf) : 0;
 	if (use_gc) {
-		const size_t need_t = (size_t)G * gc_strips * hf, need_s = (size_t)G * 2 * gc_strips * n_seg;
+		const size_t need_t = (size_t)G * gc_strips * hf, need_s = (size_t)G * gc_check_scratch_words(gc_strips, n_seg, wf);
 		if (need_t > ctx->striptot_words || need_s > ctx->gc_scratch_words) {
 			CK(ctx, cudaDeviceSynchronize());
 			const size_t nt = std::max(need_t, ctx->striptot_words), nsc = std::max(need_s, ctx->gc_scratch_words);
@@ -1487,7 +1487,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			ctx->striptot_words = ctx->gc_scratch_words = 0;
 			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
 				CK(ctx, cudaMalloc(&ctx->striptot[l], nt * 4));
-				CK(ctx, cudaMalloc(&ctx->gc_scratch[l], nsc * 8));
+				CK(ctx, cudaMalloc(&ctx->gc_scratch[l], nsc * 4));
 			}
 			ctx->striptot_words = nt;
 			ctx->gc_scratch_words = nsc;
@@ -1748,7 +1748,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
 				Stage st(ctx, "sat_check", use_gc ? 3 : 2, s);
 				if (use_gc) {
-					CK(ctx, (cudaError_t)launch_sat_check_g(s, r, segsum, segmax, ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf, g, flag));
+					CK(ctx, (cudaError_t)launch_sat_check_g(s, grad_circ_check(r, segsum, segmax, ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf), wf, hf, g, flag));
 					k_sat_fix_clear<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
 				} else {
 					k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
@@ -1812,16 +1812,8 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			Stage st(ctx, "peaks_emit", 1, s);
 			if (defer_fallback) {
 				GcCheck gc;
-				if (use_gc) {
-					gc.segsum = ctx->segsum[lane];
-					gc.segmax = ctx->segmax[lane];
-					gc.striptot = ctx->striptot[lane];
-					gc.scratch = ctx->gc_scratch[lane];
-					gc.n_seg = n_seg;
-					gc.seg_rows = seg;
-					gc.sw = grad_circ_strip_width(p->circle_radius);
-					gc.n_strips = gc_strips;
-				}
+				if (use_gc)
+					gc = grad_circ_check(p->circle_radius, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf);
 				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
 				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22, ctx->segsum[lane], ctx->segmax[lane], n_seg,
 				                       flag, gc);
