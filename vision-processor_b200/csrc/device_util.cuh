@@ -193,12 +193,12 @@ struct GcCheck {
 	const float* segsum = nullptr;
 	const float* segmax = nullptr;
 	const int32_t* striptot = nullptr; /* nullptr: not the fused gradient + circularity flow */
-	float* scratch = nullptr;          /* gc_check_scratch_words() 4-byte words per frame */
 	int n_seg = 0, seg_rows = 0, sw = 0, n_strips = 0;
 };
-__host__ __device__ inline size_t gc_check_scratch_words(int n_strips, int n_seg, int w) { return (size_t)2 * n_strips * n_seg + (size_t)n_seg * w; }
+constexpr int GC_CHECK_MAX_STRIPS = 512;
 
-/* The exactness bound of the reference's summed-area table for one frame from what k_grad_circ leaves behind:
+/* The exactness bound of the reference's summed-area table for ONE ROW SEGMENT k of one frame from what k_grad_circ leaves
+ * behind:
  *   S(c, k), A(c, k)   per column c and row segment k: the column sum of gradDot over the segment and the largest magnitude
  *                      the running sum reached on the way (segsum, segmax: n_seg x w floats per frame),
  *   P(s, y)            per strip s (the `sw` output columns of one warp) and row y: the sum of gradDot over the strip's columns
@@ -207,70 +207,73 @@ __host__ __device__ inline size_t gc_check_scratch_words(int n_strips, int n_seg
  *   SAT(x, y) = sum_{s' < s} [carry(s', k) + P(s', y)]                                      exact: the strips to the left
  *             + sum_{c in s, c <= x} [carry(c, k) + running column sum inside segment k]      carry(., k) = the sums of the segments above
  *   |SAT(x, y)| <= max_{y in k} |left(s, y)| + max_{x in s} |prefix of the column carries| + sum_{c in s} A(c, k).
- * Called by a whole CTA (a multiple of 32 threads); every thread returns the same answer: true when some |SAT| -- and with
- * it possibly a row prefix sum, |RS| <= 2 max |SAT| -- may have reached SAT_EXACT_LIMIT.  About twice the true maximum on
- * camera-like frames.  fp32 throughout: integer values are exact below 2^24, and any term that is not is four times
- * the limit already. */
-__device__ __forceinline__ bool sat_bound_exceeded_g(const GcCheck& gc, int w, int h, int f)
+ * Called by a whole CTA (a multiple of 32 threads, one CTA per frame and segment, nothing shared between them); every
+ * thread returns the same answer: true when some |SAT| of the segment -- and with it possibly a row prefix sum,
+ * |RS| <= 2 max |SAT| -- may have reached SAT_EXACT_LIMIT.  About twice the true maximum on camera-like frames.  fp32
+ * throughout: integer values are exact below 2^24, and any term that is not is four times the limit already. */
+__device__ __forceinline__ bool sat_bound_exceeded_g(const GcCheck& gc, int w, int h, int f, int k)
 {
-	const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+	__shared__ float strip_carry[GC_CHECK_MAX_STRIPS]; /* what the segments above add to strip s */
+	__shared__ unsigned left_max[GC_CHECK_MAX_STRIPS]; /* max over the segment's rows of |SAT| along the LEFT edge of strip s (float bits) */
+	__shared__ float in_strip[GC_CHECK_MAX_STRIPS];    /* the two in-strip terms */
+	const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, n_warps = nt >> 5;
 	const int n_seg = gc.n_seg, seg_rows = gc.seg_rows, n_strips = gc.n_strips;
 	const int32_t* __restrict__ P = gc.striptot + (size_t)f * n_strips * h;
 	const float* __restrict__ S = gc.segsum + (size_t)f * n_seg * w;
 	const float* __restrict__ A = gc.segmax + (size_t)f * n_seg * w;
-	float* __restrict__ strip_carry = gc.scratch + (size_t)f * gc_check_scratch_words(n_strips, n_seg, w); /* [s][k] */
-	unsigned* __restrict__ left_max = reinterpret_cast<unsigned*>(strip_carry + (size_t)n_strips * n_seg); /* [s][k], bits of a non-negative float */
-	float* __restrict__ col_carry = strip_carry + (size_t)2 * n_strips * n_seg;                             /* [k][x] */
-	const int n_pairs = n_strips * n_seg;
-	for (int s = tid; s < n_strips; s += nt) { /* what the segments above segment k add to strip s */
-		float c = 0.0f;
-		for (int k = 0; k < n_seg; k++) {
-			strip_carry[s * n_seg + k] = c;
-			left_max[s * n_seg + k] = 0u;
-			c += (float)P[(size_t)s * h + (min((k + 1) * seg_rows, h) - 1)];
-		}
-	}
-	for (int x = tid; x < w; x += nt) { /* ... and to column x */
+	const int y_begin = k * seg_rows, y_end = min(y_begin + seg_rows, h);
+	for (int s = tid; s < n_strips; s += nt) {
 		float c = 0.0f;
 #pragma unroll 4
-		for (int k = 0; k < n_seg; k++) {
-			col_carry[(size_t)k * w + x] = c;
-			c += S[(size_t)k * w + x];
+		for (int q = 0; q < k; q++) /* the last row of every segment above holds that segment's strip total */
+			c += (float)P[(size_t)s * h + (min((q + 1) * seg_rows, h) - 1)];
+		strip_carry[s] = c;
+		left_max[s] = 0u;
+	}
+	/* in-strip terms: one warp per strip, two columns per lane (sw <= 64) */
+	for (int s = wid; s < n_strips; s += n_warps) {
+		const int x0 = s * gc.sw + 2 * lane;
+		float c0 = 0.0f, c1 = 0.0f, a = 0.0f;
+		const bool in0 = 2 * lane < gc.sw && x0 < w, in1 = 2 * lane + 1 < gc.sw && x0 + 1 < w;
+#pragma unroll 4
+		for (int q = 0; q < k; q++) {
+			c0 += in0 ? S[(size_t)q * w + x0] : 0.0f;
+			c1 += in1 ? S[(size_t)q * w + x0 + 1] : 0.0f;
 		}
+		a = (in0 ? A[(size_t)k * w + x0] : 0.0f) + (in1 ? A[(size_t)k * w + x0 + 1] : 0.0f);
+		float incl = c0 + c1; /* inclusive prefix over the lanes' column pairs */
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const float t = __shfl_up_sync(0xffffffffu, incl, d);
+			if (lane >= d)
+				incl += t;
+		}
+		float pre_max = fmaxf(fabsf(incl - c1), fabsf(incl)); /* the prefixes ending at this lane's first and second column */
+#pragma unroll
+		for (int d = 16; d; d >>= 1) {
+			pre_max = fmaxf(pre_max, __shfl_xor_sync(0xffffffffu, pre_max, d));
+			a += __shfl_xor_sync(0xffffffffu, a, d);
+		}
+		if (lane == 0)
+			in_strip[s] = pre_max + a;
 	}
 	__syncthreads();
-	/* the summed-area table along the right edge of every strip, row by row: one thread per row walks the strips */
-	const bool warp_rows_share_segment = (seg_rows & 31) == 0;
-	for (int y0 = 0; y0 < h; y0 += nt) {
+	/* the summed-area table along the left edge of every strip, row by row: one thread per row walks the strips */
+	for (int y0 = y_begin; y0 < y_end; y0 += nt) {
 		const int y = y0 + tid;
-		const int k = min(y, h - 1) / seg_rows;
 		float acc = 0.0f;
 		for (int s = 0; s + 1 < n_strips; s++) {
-			if (y < h)
-				acc += strip_carry[s * n_seg + k] + (float)P[(size_t)s * h + y];
-			const unsigned mine = y < h ? __float_as_uint(fabsf(acc)) : 0u;
-			if (warp_rows_share_segment) { /* y0 and nt are multiples of 32: the 32 rows of a warp lie in one segment */
-				const unsigned m = __reduce_max_sync(0xffffffffu, mine);
-				if (lane == 0 && m)
-					atomicMax(left_max + (s + 1) * n_seg + k, m);
-			} else if (mine) {
-				atomicMax(left_max + (s + 1) * n_seg + k, mine);
-			}
+			if (y < y_end)
+				acc += strip_carry[s] + (float)P[(size_t)s * h + y];
+			const unsigned m = __reduce_max_sync(0xffffffffu, y < y_end ? __float_as_uint(fabsf(acc)) : 0u);
+			if (lane == 0 && m)
+				atomicMax(left_max + s + 1, m);
 		}
 	}
 	__syncthreads();
 	bool bad = false;
-	for (int p = tid; p < n_pairs; p += nt) {
-		const int s = p / n_seg, k = p - s * n_seg;
-		const int x0 = s * gc.sw, x1 = min(x0 + gc.sw, w);
-		float pre = 0.0f, in_pre = 0.0f, in_a = 0.0f;
-		for (int x = x0; x < x1; x++) {
-			pre += col_carry[(size_t)k * w + x];
-			in_pre = fmaxf(in_pre, fabsf(pre));
-			in_a += A[(size_t)k * w + x];
-		}
-		bad |= !(__uint_as_float(left_max[p]) + in_pre + in_a < (float)SAT_EXACT_LIMIT);
-	}
+	for (int s = tid; s < n_strips; s += nt)
+		bad |= !(__uint_as_float(left_max[s]) + in_strip[s] < (float)SAT_EXACT_LIMIT);
 	return __syncthreads_or(bad);
 }
 

@@ -4,15 +4,16 @@
 
 namespace vpk {
 
-/* batch path: one CTA per frame evaluates the bound and raises the frame's flag */
-__global__ void __launch_bounds__(1024) k_sat_check_g(GcCheck gc, int w, int h, int* __restrict__ flag)
+/* batch path: one CTA per (row segment, frame) evaluates the bound and raises the frame's flag */
+__global__ void __launch_bounds__(256) k_sat_check_g(GcCheck gc, int w, int h, int* __restrict__ flag)
 {
-	const int f = blockIdx.x;
-	if (sat_bound_exceeded_g(gc, w, h, f) && threadIdx.x == 0)
+	const int f = blockIdx.y;
+	if (sat_bound_exceeded_g(gc, w, h, f, blockIdx.x) && threadIdx.x == 0)
 		flag[f] = 2;
 }
 
 bool grad_circ_supported(int r, int o) { return r >= 1 && r <= GC_MAX_R && o >= 0 && o <= GC_MAX_OFFSET && 2 * o <= r + 2; }
+static_assert(gc_strip_width(GC_MAX_R) >= 32 && gc_strip_width(1) <= 64, "the bound check walks a strip with two columns per lane");
 
 int grad_circ_strip_width(int r) { return gc_strip_width(r); }
 
@@ -57,13 +58,12 @@ int launch_grad_circ(cudaStream_t stream, int r, const uint32_t* flat, float* gr
 
 int grad_circ_strips(int r, int w) { return (w + gc_strip_width(r) - 1) / gc_strip_width(r); }
 
-GcCheck grad_circ_check(int r, const float* segsum, const float* segmax, const int32_t* striptot, float* scratch, int seg_rows, int w, int h)
+GcCheck grad_circ_check(int r, const float* segsum, const float* segmax, const int32_t* striptot, int seg_rows, int w, int h)
 {
 	GcCheck gc;
 	gc.segsum = segsum;
 	gc.segmax = segmax;
 	gc.striptot = striptot;
-	gc.scratch = scratch;
 	gc.seg_rows = seg_rows;
 	gc.n_seg = (h + seg_rows - 1) / seg_rows;
 	gc.sw = gc_strip_width(r);
@@ -73,7 +73,7 @@ GcCheck grad_circ_check(int r, const float* segsum, const float* segmax, const i
 
 int launch_sat_check_g(cudaStream_t stream, const GcCheck& gc, int w, int h, int n_frames, int* flag)
 {
-	k_sat_check_g<<<n_frames, 1024, 0, stream>>>(gc, w, h, flag);
+	k_sat_check_g<<<dim3(gc.n_seg, n_frames), 256, 0, stream>>>(gc, w, h, flag);
 	return (int)cudaGetLastError();
 }
 

@@ -84,28 +84,27 @@ __device__ __forceinline__ uint2 lds64(const uint32_t* p)
 	return v;
 }
 
-/* sum_{j=1..N} P(lane + j) by doubling (N <= 7) */
+/* sum_{j=1..N} P(lane + j), N <= 6: shuffles that do not depend on one another wherever that costs no extra shuffle (the
+ * kernel waits on these chains: two dependent steps at most) */
 template <int N>
 __device__ __forceinline__ float pairs_right(float P)
 {
 	if constexpr (N == 0)
 		return 0.0f;
-	const float w1 = __shfl_down_sync(0xffffffffu, P, 1);
+	const float p1 = __shfl_down_sync(0xffffffffu, P, 1);
 	if constexpr (N == 1)
-		return w1;
-	const float w2 = __fadd_rn(w1, __shfl_down_sync(0xffffffffu, w1, 1));
+		return p1;
+	const float p12 = __fadd_rn(p1, __shfl_down_sync(0xffffffffu, P, 2));
 	if constexpr (N == 2)
-		return w2;
+		return p12;
 	if constexpr (N == 3)
-		return __fadd_rn(w2, __shfl_down_sync(0xffffffffu, w1, 2));
-	const float w4 = __fadd_rn(w2, __shfl_down_sync(0xffffffffu, w2, 2));
+		return __fadd_rn(p12, __shfl_down_sync(0xffffffffu, P, 3));
+	const float p1234 = __fadd_rn(p12, __shfl_down_sync(0xffffffffu, p12, 2));
 	if constexpr (N == 4)
-		return w4;
+		return p1234;
 	if constexpr (N == 5)
-		return __fadd_rn(w4, __shfl_down_sync(0xffffffffu, w1, 4));
-	if constexpr (N == 6)
-		return __fadd_rn(w4, __shfl_down_sync(0xffffffffu, w2, 4));
-	return __fadd_rn(__fadd_rn(w4, __shfl_down_sync(0xffffffffu, w2, 4)), __shfl_down_sync(0xffffffffu, w1, 6));
+		return __fadd_rn(p1234, __shfl_down_sync(0xffffffffu, P, 5));
+	return __fadd_rn(p1234, __shfl_down_sync(0xffffffffu, p12, 4));
 }
 
 /* The horizontal window of a lane's two columns a = c0, b = c0 + 1 from the per-column sums V (exact integers):

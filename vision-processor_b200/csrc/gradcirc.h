@@ -22,9 +22,9 @@ int grad_circ_strips(int circle_radius, int w);
 int launch_grad_circ(cudaStream_t stream, int circle_radius, const uint32_t* flat, float* grad, float* circ, int w, int h, int grad_offset, int seg_rows,
                      int n_frames, float thr, float min_score, int blob_radius, int need_score, int32_t* counter, int32_t* rowcount, uint32_t* masks, int wpr,
                      float* segsum, float* segmax, int32_t* striptot);
-/* what the bound check reads (device_util.cuh: GcCheck); scratch: gc_check_scratch_words() 4-byte words per frame */
-GcCheck grad_circ_check(int circle_radius, const float* segsum, const float* segmax, const int32_t* striptot, float* scratch, int seg_rows, int w, int h);
-/* the bound itself, one CTA per frame: raises flag[f] = 2 for frames that may have left it */
+/* what the bound check reads (device_util.cuh: GcCheck) */
+GcCheck grad_circ_check(int circle_radius, const float* segsum, const float* segmax, const int32_t* striptot, int seg_rows, int w, int h);
+/* the bound itself, one CTA per row segment and frame: raises flag[f] = 2 for frames that may have left it */
 int launch_sat_check_g(cudaStream_t stream, const GcCheck& gc, int w, int h, int n_frames, int* flag);
 
 } // namespace vpk

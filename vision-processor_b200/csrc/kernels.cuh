@@ -2300,6 +2300,7 @@ __device__ __forceinline__ bool sat_bound_exceeded(const float* __restrict__ seg
 	return __syncthreads_or(bad);
 }
 
+constexpr int EMIT_MAX_ROWS = 128;
 /* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp.
  * Latency path (segsum != nullptr): the grid has ceil(w/256) more CTAs per frame, which evaluate the exactness bound of
  * the SAT next to the record warps and raise the frame's flag for the HOST to see -- the caller then redoes the frame in
@@ -2309,11 +2310,11 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
                                                     int max_matches, const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
                                                     const uint32_t* __restrict__ masks, int wpr, uint8_t* __restrict__ matches, size_t match_frame_stride,
                                                     const float* __restrict__ segsum = nullptr, const float* __restrict__ segmax = nullptr, int n_seg = 0,
-                                                    int* __restrict__ flag = nullptr, GcCheck gc = GcCheck())
+                                                    int* __restrict__ flag = nullptr, GcCheck gc = GcCheck(), int rows_per_cta = 8)
 {
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int f = blockIdx.y;
-	const int n_row_ctas = (h + 7) >> 3;
+	const int n_row_ctas = (h + rows_per_cta - 1) / rows_per_cta;
 	if (blockIdx.x >= n_row_ctas) { /* only launched when segsum is given: one thread per column */
 		/* the sibling column CTAs of this frame may raise the flag while this one runs: the CTA takes ONE snapshot, so that
 		 * every warp reaches the barrier inside sat_bound_exceeded or none does */
@@ -2323,43 +2324,62 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 		__syncthreads();
 		if (flag_seen != 0)
 			return;
-		/* fused gradient + circularity flow: ONE more CTA per frame, which evaluates the whole bound from k_grad_circ's side outputs;
+		/* fused gradient + circularity flow: one more CTA per row segment, which evaluates the segment's bound from k_grad_circ's side outputs;
 		 * row-sum flow: one CTA per 256 columns over k_circ_stream_rs's column sums of the row sums */
-		const bool bad = gc.striptot ? sat_bound_exceeded_g(gc, w, h, f)
+		const bool bad = gc.striptot ? sat_bound_exceeded_g(gc, w, h, f, blockIdx.x - n_row_ctas)
 		                             : sat_bound_exceeded(segsum, segmax, n_seg, w, f, (blockIdx.x - n_row_ctas) * 256 + threadIdx.x, w);
 		if (bad && threadIdx.x == 0)
 			flag[f] = 2;
 		return;
 	}
-	const int y = blockIdx.x * 8 + (threadIdx.x >> 5);
-	if (y >= h)
-		return;
+	/* rank of the CTA's first blob: blobs of all earlier rows, summed by the whole CTA (coalesced, one round trip deep); then
+	 * the CTA's own rows.  A batch gives a CTA many rows (few, fat CTAs: the grid of one-warp-per-row CTAs cost more to
+	 * launch than to run), a lone frame eight (every row at once). */
+	__shared__ int s_part[8], s_cnt[EMIT_MAX_ROWS], s_pre[EMIT_MAX_ROWS];
+	const int row0 = blockIdx.x * rows_per_cta;
 	const int32_t* rc = rowcount + (size_t)f * h;
-	if (rc[y] == 0)
-		return;
-	int before = 0;
-#pragma unroll 8
-	for (int k = lane; k < y; k += 32) /* independent loads: eight in flight (a lone frame waits on this chain) */
-		before += rc[k];
+	int part = 0;
+	for (int k = threadIdx.x; k < row0; k += 256)
+		part += rc[k];
 #pragma unroll
 	for (int d = 16; d; d >>= 1)
-		before += __shfl_xor_sync(0xffffffffu, before, d);
-	int rank = first_slot[f] + before;
+		part += __shfl_xor_sync(0xffffffffu, part, d);
+	if (lane == 0)
+		s_part[warp] = part;
+	if (threadIdx.x < rows_per_cta)
+		s_cnt[threadIdx.x] = row0 + threadIdx.x < h ? rc[row0 + threadIdx.x] : 0;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		int run = first_slot[f];
+		for (int k = 0; k < 8; k++)
+			run += s_part[k];
+		for (int t = 0; t < rows_per_cta; t++) {
+			s_pre[t] = run;
+			run += s_cnt[t];
+		}
+	}
+	__syncthreads();
 	const size_t fbase = (size_t)f * w * h;
-	const uint32_t* mk = masks + ((size_t)f * h + y) * wpr;
 	uint8_t* out = matches + (size_t)f * match_frame_stride;
-	for (int base = 0; base < wpr && rank < max_matches; base += 32) {
-		const uint32_t mine = base + lane < wpr ? mk[base + lane] : 0u;
-		unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
-		while (nz && rank < max_matches) {
-			const int src = __ffs(nz) - 1;
-			nz &= nz - 1;
-			uint32_t word = __shfl_sync(0xffffffffu, mine, src);
-			while (word && rank < max_matches) {
-				const int b = __ffs(word) - 1;
-				word &= word - 1;
-				emit_match(img + fbase, circ + fbase, w, h, (base + src) * 32 + b, y, radius, out + 22 * (size_t)rank, lane);
-				rank++;
+	for (int t = warp; t < rows_per_cta; t += 8) {
+		if (s_cnt[t] == 0)
+			continue;
+		const int y = row0 + t;
+		int rank = s_pre[t];
+		const uint32_t* mk = masks + ((size_t)f * h + y) * wpr;
+		for (int base = 0; base < wpr && rank < max_matches; base += 32) {
+			const uint32_t mine = base + lane < wpr ? mk[base + lane] : 0u;
+			unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+			while (nz && rank < max_matches) {
+				const int src = __ffs(nz) - 1;
+				nz &= nz - 1;
+				uint32_t word = __shfl_sync(0xffffffffu, mine, src);
+				while (word && rank < max_matches) {
+					const int b = __ffs(word) - 1;
+					word &= word - 1;
+					emit_match(img + fbase, circ + fbase, w, h, (base + src) * 32 + b, y, radius, out + 22 * (size_t)rank, lane);
+					rank++;
+				}
 			}
 		}
 	}

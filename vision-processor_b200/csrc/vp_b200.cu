@@ -173,8 +173,7 @@ struct vp_ctx {
 	bool gc_attr = false;
 	bool sat_free = true; /* circularity straight from the row sums: no column scan, no materialised SAT (needs stream_circ, !fused_sat) */
 	int32_t* striptot[MAX_LANES] = {}; /* per lane: k_grad_circ's per-row strip sums of gradDot (frames of the group x strips x rows) */
-	float* gc_scratch[MAX_LANES] = {};
-	size_t striptot_words = 0, gc_scratch_words = 0;
+	size_t striptot_words = 0;
 	float* segsum[MAX_LANES] = {}; /* per lane: column sums of the row sums per (frame of the group, row segment) */
 	float* segmax[MAX_LANES] = {};
 	size_t seg_words = 0;
@@ -485,9 +484,12 @@ int launch_peaks_emit(vp_ctx* ctx, cudaStream_t stream, const uint32_t* flat, co
                       const float* segsum = nullptr, const float* segmax = nullptr, int n_seg = 0, int* flag = nullptr, GcCheck gc = GcCheck())
 {
 	/* segsum given: more CTAs per frame check the exactness bound of the SAT next to the record warps (see k_peaks_emit):
-	 * one per 256 columns for the row-sum flow, ONE for the fused gradient + circularity kernel */
-	k_peaks_emit<<<dim3(cdiv(h, 8) + (segsum ? (gc.striptot ? 1 : cdiv(w, 256)) : 0), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount, masks,
-	                                                                                          cdiv(w, 32), matches, match_stride, segsum, segmax, n_seg, flag, gc);
+	 * one per 256 columns for the row-sum flow, one per row segment for the fused gradient + circularity kernel.
+	 * Rows per CTA: 8 for a few frames (every row at once), 64 for a batch (a grid of 8-row CTAs took longer to launch than to run) */
+	const int rpc = n >= 16 ? 64 : 8;
+	k_peaks_emit<<<dim3(cdiv(h, rpc) + (segsum ? (gc.striptot ? gc.n_seg : cdiv(w, 256)) : 0), n), 256, 0, stream>>>(flat, circ, w, h, radius, max_matches, first_slot, rowcount,
+	                                                                                                      masks, cdiv(w, 32), matches, match_stride, segsum, segmax, n_seg,
+	                                                                                                      flag, gc, rpc);
 	return check_launch(ctx, "k_peaks_emit");
 }
 
@@ -570,22 +572,52 @@ __global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict_
 	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
 }
 
-/* flow of the fused gradient + circularity kernel: the bound has been evaluated (k_sat_check_g / k_peaks_emit); a flagged frame
- * forgets what the fast pass published and gets its SAT in the reference's sequential order for k_circ_stream's literal path */
-__global__ void __launch_bounds__(1024) k_sat_fix_clear(const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
-                                                        const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                                                        uint32_t* __restrict__ masks, int wpr)
+/* Flow of the fused gradient + circularity kernel: the bound has been evaluated (k_sat_check_g / k_peaks_emit).  ONE launch
+ * with one CTA per frame, which exits at once for a clean frame.  A flagged frame (never seen on camera images) forgets what the
+ * fast pass published and is redone entirely here, in the reference's order: sequential summed-area table (satHorizontal.cl,
+ * satVertical.cl), the literal 16-tap circularity with IEEE division (satBlobCenter.cl:37-41) and the peak classification
+ * (blobList.cl:38-81).  Slow (about a millisecond for a 1224x1024 frame) and rare; what matters is that clean frames do not
+ * pay for it -- the previous flow launched a full-size grid of the streaming kernel just to have every CTA exit. */
+__global__ void __launch_bounds__(1024) k_fallback_frame(const uint32_t* __restrict__ flat, const float* __restrict__ grad, float* __restrict__ hor,
+                                                         float* __restrict__ sat, float* __restrict__ circ, int w, int h, int r, float thr, float min_score,
+                                                         int radius, int need_score, const int* __restrict__ flag, int32_t* __restrict__ counter,
+                                                         int32_t* __restrict__ rowcount, uint32_t* __restrict__ masks, int wpr)
 {
 	const int f = blockIdx.x;
 	if (flag[f] == 0)
 		return;
+	const size_t fbase = (size_t)f * w * h;
 	for (int i = threadIdx.x; i < h * wpr; i += 1024)
 		masks[(size_t)f * h * wpr + i] = 0u;
 	for (int i = threadIdx.x; i < h; i += 1024)
 		rowcount[(size_t)f * h + i] = 0;
 	if (threadIdx.x < 3)
 		counter[3 * f + threadIdx.x] = 0;
-	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
+	sat_fix_frame(grad, hor, sat, w, h, fbase);
+	__syncthreads();
+	const float div = (float)(r * r);
+	for (int i = threadIdx.x; i < w * h; i += 1024) {
+		const int y = i / w, x = i - y * w;
+		circ[fbase + i] = circle_px(sat + fbase, w, h, x, y, r, div);
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const float* cf = circ + fbase;
+	int nb = 0, ns = 0, np = 0;
+	for (int sg = warp; sg < h * wpr; sg += 32) { /* a warp = 32 consecutive pixels of a row */
+		const int y = sg / wpr, x = (sg - y * wpr) * 32 + lane;
+		int cls = 0;
+		if (x < w) {
+			const float c = __ldcg(cf + (size_t)y * w + x); /* written above by this CTA: not through the read-only path */
+			if (!(c < thr)) {
+				const float lf = __ldcg(cf + (size_t)y * w + max(x - 1, 0)), rt = __ldcg(cf + (size_t)y * w + min(x + 1, w - 1));
+				const float up = __ldcg(cf + (size_t)max(y - 1, 0) * w + x), dn = __ldcg(cf + (size_t)min(y + 1, h - 1) * w + x);
+				cls = classify_px(flat + fbase, w, h, x, y, radius, thr, min_score, need_score, c, lf, rt, up, dn);
+			}
+		}
+		publish_segment(cls, lane, rowcount + (size_t)f * h, masks + (size_t)f * h * wpr, wpr, y, sg - y * wpr, nb, ns, np);
+	}
+	publish_counters(lane, counter + 3 * f, nb, ns, np);
 }
 
 /* rows per CTA of the streaming circularity kernels: 128 (few halo rows per segment) whenever that already gives the GPU two
@@ -747,7 +779,6 @@ void vp_ctx_destroy(vp_ctx* c)
 		cudaFree(c->segsum[l]);
 		cudaFree(c->segmax[l]);
 		cudaFree(c->striptot[l]);
-		cudaFree(c->gc_scratch[l]);
 		if (l > 0 && c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
 		if (c->lane_done[l]) cudaEventDestroy(c->lane_done[l]);
 	}
@@ -1474,23 +1505,17 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	}
 	const int gc_strips = use_gc ? grad_circ_strips(p->circle_radius, wf) : 0;
 	if (use_gc) {
-		const size_t need_t = (size_t)G * gc_strips * hf, need_s = (size_t)G * gc_check_scratch_words(gc_strips, n_seg, wf);
-		if (need_t > ctx->striptot_words || need_s > ctx->gc_scratch_words) {
+		const size_t need_t = (size_t)G * gc_strips * hf;
+		if (need_t > ctx->striptot_words) {
 			CK(ctx, cudaDeviceSynchronize());
-			const size_t nt = std::max(need_t, ctx->striptot_words), nsc = std::max(need_s, ctx->gc_scratch_words);
 			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
 				cudaFree(ctx->striptot[l]);
-				cudaFree(ctx->gc_scratch[l]);
 				ctx->striptot[l] = nullptr;
-				ctx->gc_scratch[l] = nullptr;
 			}
-			ctx->striptot_words = ctx->gc_scratch_words = 0;
-			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
-				CK(ctx, cudaMalloc(&ctx->striptot[l], nt * 4));
-				CK(ctx, cudaMalloc(&ctx->gc_scratch[l], nsc * 4));
-			}
-			ctx->striptot_words = nt;
-			ctx->gc_scratch_words = nsc;
+			ctx->striptot_words = 0;
+			for (int l = 0; l < vp_ctx::MAX_LANES; l++)
+				CK(ctx, cudaMalloc(&ctx->striptot[l], need_t * 4));
+			ctx->striptot_words = need_t;
 		}
 	}
 	/* single-pass gradient + SAT: a strip of srows rows x full width lives in shared memory */
@@ -1746,25 +1771,25 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			if (!defer_fallback) {
 				/* the exactness bound of the summed-area table, checked after the fact; frames that left it (or whose row sums
 				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
-				Stage st(ctx, "sat_check", use_gc ? 3 : 2, s);
+				Stage st(ctx, "sat_check", 2, s);
 				if (use_gc) {
-					CK(ctx, (cudaError_t)launch_sat_check_g(s, grad_circ_check(r, segsum, segmax, ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf), wf, hf, g, flag));
-					k_sat_fix_clear<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
+					CK(ctx, (cudaError_t)launch_sat_check_g(s, grad_circ_check(r, segsum, segmax, ctx->striptot[lane], seg, wf, hf), wf, hf, g, flag));
+					k_fallback_frame<<<g, 1024, 0, s>>>(flat, grad, (float*)rowsum, sat, circ, wf, hf, r, p->circ_threshold, p->min_score, p->blob_radius, ns, flag,
+					                                    counter, rowcount, masks, wpr);
 				} else {
 					k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
-				}
 #define VP_CSF(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, fb_seg), g);                                                          \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, fb_seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
 		                                       rowcount, masks, wpr, 1);                                                       \
 	} break;
-				const int fb_seg = 128; /* the fallback pass picks its own segments: nothing is handed over by rows */
-				switch (r) {
-					VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
-				}
+					switch (r) {
+						VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
+					}
 #undef VP_CSF
+				}
 				if ((rc = check_launch(ctx, "sat_check/fallback"))) return rc;
 			}
 		} else if (fused_circ) {
@@ -1813,7 +1838,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			if (defer_fallback) {
 				GcCheck gc;
 				if (use_gc)
-					gc = grad_circ_check(p->circle_radius, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane], ctx->gc_scratch[lane], seg, wf, hf);
+					gc = grad_circ_check(p->circle_radius, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane], seg, wf, hf);
 				rc = launch_peaks_emit(ctx, s, flat, circ, wf, hf, g, p->blob_radius, p->max_blobs, ctx->first_slot + f0, rowcount, masks,
 				                       (uint8_t*)d_matches + (size_t)f0 * p->max_blobs * 22, (size_t)p->max_blobs * 22, ctx->segsum[lane], ctx->segmax[lane], n_seg,
 				                       flag, gc);
@@ -1849,23 +1874,25 @@ static int redo_flagged(vp_ctx* ctx, int n_frames, const vp_params* p, uint8_t* 
 	uint32_t* flat = (uint32_t*)d_flat;
 	float* sat = ctx->sat[0];
 	int rc;
-	Stage st(ctx, "sat_check", 3, s);
-	if (use_gc) /* the flags are final: the bound was evaluated next to the record kernel */
-		k_sat_fix_clear<<<n_frames, 1024, 0, s>>>(d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount, ctx->masks, wpr);
-	else
+	Stage st(ctx, "sat_check", use_gc ? 2 : 3, s);
+	if (use_gc) { /* the flags are final: the bound was evaluated next to the record kernel */
+		k_fallback_frame<<<n_frames, 1024, 0, s>>>(flat, d_grad, (float*)ctx->rowsum[0], sat, d_circ, wf, hf, r, p->circ_threshold, p->min_score, p->blob_radius, ns,
+		                                           flags, d_counter, ctx->rowcount, ctx->masks, wpr);
+	} else {
 		k_sat_check_fix<<<n_frames, 1024, 0, s>>>(ctx->segsum[0], ctx->segmax[0], n_seg, d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount,
 		                                          ctx->masks, wpr);
 #define VP_CSF(RR)                                                                                                             \
 	case RR: {                                                                                                                 \
 		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, 128), n_frames);                                                      \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, 128, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, n_frames);                                                              \
+		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
 		                                       ctx->rowcount, ctx->masks, wpr, 1);                                             \
 	} break;
-	switch (r) {
-		VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
-	}
+		switch (r) {
+			VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
+		}
 #undef VP_CSF
+	}
 	if ((rc = check_launch(ctx, "sat_check/fallback (redo)"))) return rc;
 	return launch_peaks_emit(ctx, s, flat, d_circ, wf, hf, n_frames, p->blob_radius, p->max_blobs, ctx->first_slot, ctx->rowcount, ctx->masks,
 	                         (uint8_t*)d_matches, (size_t)p->max_blobs * 22);
@@ -2061,7 +2088,7 @@ static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p,
 		}
 	}
 	const void* ptrs[18] = { s.raw, s.flat, s.grad, s.circ, s.results, s.results_host, ctx->rowsum[0], ctx->sat[0], ctx->segsum[0], ctx->segmax[0],
-		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->striptot[0], ctx->gc_scratch[0] };
+		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->striptot[0], nullptr };
 	memcpy(fp->ptr, ptrs, sizeof ptrs);
 	const int knobs[10] = { ctx->staged_reproject, ctx->sat_free, ctx->stream_circ, ctx->fused_sat, ctx->hoist_chunk, ctx->group, ctx->lanes, ctx->strips,
 		                    ctx->profiling, ctx->fused_gc };
