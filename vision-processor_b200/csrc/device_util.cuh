@@ -258,16 +258,26 @@ __device__ __forceinline__ bool sat_bound_exceeded_g(const GcCheck& gc, int w, i
 			in_strip[s] = pre_max + a;
 	}
 	__syncthreads();
-	/* the summed-area table along the left edge of every strip, row by row: one thread per row walks the strips */
+	/* the summed-area table along the left edge of every strip, row by row: one thread per row walks the strips, eight loads
+	 * in flight at a time */
 	for (int y0 = y_begin; y0 < y_end; y0 += nt) {
 		const int y = y0 + tid;
+		const bool in = y < y_end;
 		float acc = 0.0f;
-		for (int s = 0; s + 1 < n_strips; s++) {
-			if (y < y_end)
-				acc += strip_carry[s] + (float)P[(size_t)s * h + y];
-			const unsigned m = __reduce_max_sync(0xffffffffu, y < y_end ? __float_as_uint(fabsf(acc)) : 0u);
-			if (lane == 0 && m)
-				atomicMax(left_max + s + 1, m);
+		for (int s0 = 0; s0 + 1 < n_strips; s0 += 8) {
+			int v[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				v[j] = in && s0 + j + 1 < n_strips ? __ldg(P + (size_t)(s0 + j) * h + y) : 0;
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				if (s0 + j + 1 < n_strips) { /* CTA-uniform */
+					acc += strip_carry[s0 + j] + (float)v[j];
+					const unsigned m = __reduce_max_sync(0xffffffffu, in ? __float_as_uint(fabsf(acc)) : 0u);
+					if (lane == 0 && m)
+						atomicMax(left_max + s0 + j + 1, m);
+				}
+			}
 		}
 	}
 	__syncthreads();

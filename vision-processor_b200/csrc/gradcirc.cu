@@ -2,6 +2,9 @@
 #include "gradcirc.cuh"
 #include "gradcirc.h"
 
+#include <cstring>
+#include <mutex>
+
 namespace vpk {
 
 /* batch path: one CTA per (row segment, frame) evaluates the bound and raises the frame's flag */
@@ -18,6 +21,40 @@ static_assert(gc_strip_width(GC_MAX_R) >= 32 && gc_strip_width(1) <= 64, "the bo
 int grad_circ_strip_width(int r) { return gc_strip_width(r); }
 
 #define VP_GC_ALL(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+
+namespace {
+using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiled g_encode = nullptr;
+std::once_flag g_encode_once;
+
+/* the driver's tensor-map encoder through the runtime (libvp_b200.so links cudart only) */
+EncodeTiled encode_tiled()
+{
+	std::call_once(g_encode_once, [] {
+		void* fn = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+			g_encode = (EncodeTiled)fn;
+	});
+	return g_encode;
+}
+
+/* the flat images of one launch as a rank-3 tensor (column, row, frame) of 32-bit pixels, box = one staged slot */
+int flat_tensor_map(CUtensorMap* map, const uint32_t* flat, int w, int h, int n_frames, int r)
+{
+	EncodeTiled enc = encode_tiled();
+	if (!enc)
+		return (int)cudaErrorNotSupported;
+	const cuuint64_t dims[3] = { (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_frames };
+	const cuuint64_t strides[2] = { (cuuint64_t)w * 4, (cuuint64_t)w * h * 4 };
+	const cuuint32_t box[3] = { (cuuint32_t)gc_row_bytes(r) / 4, (cuuint32_t)(r + 2), 1 };
+	const cuuint32_t estr[3] = { 1, 1, 1 };
+	const CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)flat, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+	                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	return rc == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+} // namespace
 
 int grad_circ_prepare()
 {
@@ -37,15 +74,22 @@ int launch_grad_circ(cudaStream_t stream, int r, const uint32_t* flat, float* gr
                      float* segmax, int32_t* striptot)
 {
 	const int n_seg = (h + seg_rows - 1) / seg_rows;
+	alignas(64) CUtensorMap tmap;
+	memset(&tmap, 0, sizeof tmap);
+	if ((w & 3) == 0) { /* else no strip takes the TMA path (k_grad_circ: `bulk`) and the map is never touched */
+		const int rc = flat_tensor_map(&tmap, flat, w, h, n_frames, r);
+		if (rc)
+			return rc;
+	}
 #define VP_GC_LAUNCH(RR)                                                                                                       \
 	case RR: {                                                                                                                 \
 		const int strips = (w + gc_strip_width(RR) - 1) / gc_strip_width(RR);                                                  \
 		const dim3 grid((strips + GC_WARPS - 1) / GC_WARPS, n_seg, n_frames);                                                  \
 		if (o & 1)                                                                                                             \
-			k_grad_circ<RR, true><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius,    \
+			k_grad_circ<RR, true><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(tmap, flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius, \
 			                                                                         need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips); \
 		else                                                                                                                   \
-			k_grad_circ<RR, false><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius,   \
+			k_grad_circ<RR, false><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(tmap, flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius, \
 			                                                                          need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips); \
 	} break;
 	switch (r) {

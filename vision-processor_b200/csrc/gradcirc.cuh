@@ -28,13 +28,17 @@
  */
 #pragma once
 
+#include <cuda.h>
+
 #include "device_util.cuh"
 
 namespace vpk {
 
 constexpr int GC_OH = 4;                /* columns staged to the left and right of a strip's 64 (gradient offset <= 4) */
-constexpr int GC_NW = 64 + 2 * GC_OH;   /* words per staged row */
-constexpr int GC_ROWBYTES = GC_NW * 4;  /* 288: a multiple of 16, as cp.async.bulk wants */
+constexpr int GC_NW = 64 + 2 * GC_OH;   /* words of a staged row that are read */
+/* bytes from one staged row to the next = width of the TMA box: 288 (the 72 words) when a slot of D = R+2 such rows is a multiple
+ * of 128 bytes (the alignment of a TMA destination), else 384 */
+__host__ __device__ constexpr int gc_row_bytes(int R) { return ((R + 2) * GC_NW * 4) % 128 == 0 ? GC_NW * 4 : 384; }
 constexpr int GC_WARPS = 4;
 constexpr int GC_MAX_R = 12;
 constexpr int GC_MAX_OFFSET = GC_OH;
@@ -44,9 +48,9 @@ constexpr int GC_MAX_OFFSET = GC_OH;
 __host__ __device__ constexpr int gc_halo_left(int R) { return (((R & 1) ? R + 3 : R + 2) + 3) & ~3; }
 /* output columns per strip: circ(x+1) of the last one needs V up to column x+1+R inside the 64 */
 __host__ __device__ constexpr int gc_strip_width(int R) { return (62 - R - gc_halo_left(R)) & ~3; }
-/* rows of the per-warp ring: three slots of D = R+2 rows and GC_OH mirror rows at both ends (see k_grad_circ) */
-__host__ __device__ constexpr int gc_ring_rows(int R) { return 3 * (R + 2) + 2 * GC_OH; }
-__host__ __device__ constexpr size_t gc_smem_bytes(int R) { return (size_t)GC_WARPS * gc_ring_rows(R) * GC_ROWBYTES + 128; }
+/* rows of the per-warp ring: three slots of D = R+2 rows and a mirror slot below them (see k_grad_circ) */
+__host__ __device__ constexpr int gc_ring_rows(int R) { return 4 * (R + 2); }
+__host__ __device__ constexpr size_t gc_smem_bytes(int R) { return (size_t)GC_WARPS * gc_ring_rows(R) * gc_row_bytes(R) + 128; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
@@ -67,6 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 	             "bra WAIT_%=;\n"
 	             "DONE_%=:\n"
 	             "}" ::"r"(smem_u32(bar)), "r"(parity)
+	             : "memory");
+}
+/* a box of D rows of one frame of the flat images -> shared memory in ONE instruction (UTMALDG); coordinates in elements:
+ * column, row, frame.  Elements outside the image arrive as zeros (the caller only uses the box where that cannot matter). */
+__device__ __forceinline__ void tensor_copy_g2s(void* smem_dst, const void* tmap, int x, int y, int z, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+	             "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
 	             : "memory");
 }
 /* one row of a flat image -> shared memory through the TMA engine (UBLKCP); completes `bytes` on the mbarrier */
@@ -159,25 +171,28 @@ __device__ __forceinline__ T* bump(T* p, unsigned bytes)
 	return reinterpret_cast<T*>(r);
 }
 
-/* Ring of staged flat rows of one warp: 3 slots of D rows -- the group being computed (plus `o` rows either side of it) and the
- * next group in flight -- and GC_OH mirror rows at both ends, so that the rows a group reads (relative rows -o .. D-1+o of its
- * slot) are contiguous in shared memory and every tap address is the group's base plus an immediate. */
+/* Ring of staged flat rows of one warp: three slots of D rows and a mirror slot below them.  Group g (gradient rows t .. t+D-1)
+ * owns logical slot g % 3, which holds the D rows it ADDS to what is staged: image rows t+o .. t+o+D-1.  The other rows it reads,
+ * t-o .. t+o-1, are the tail of the previous group's slot, which lies directly below in shared memory -- for logical slot 0
+ * that is the mirror, a second copy of logical slot 2.  So every tap address is the slot's base plus an immediate, and a group
+ * is staged by ONE TMA tensor copy of D rows (two for logical slot 2), one group ahead of the arithmetic.  Groups whose rows
+ * leave the image at the top or bottom need the edge row repeated (CLAMP_TO_EDGE), which the tensor copy cannot do: those few
+ * are staged row by row (cp.async.bulk with a clamped row); strips at the left/right image edge lane by lane (cp.async). */
 template <int R, bool O_ODD>
 __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
-    k_grad_circ(const uint32_t* __restrict__ flat, float* __restrict__ grad, float* __restrict__ circ_out, int w, int h, int o, int seg_rows, float thr,
-                float min_score, int radius, int need_score, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount, uint32_t* __restrict__ masks,
-                int wpr, float* __restrict__ segsum, float* __restrict__ segmax, int32_t* __restrict__ striptot, int n_strips)
+    k_grad_circ(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ flat, float* __restrict__ grad, float* __restrict__ circ_out, int w, int h,
+                int o, int seg_rows, float thr, float min_score, int radius, int need_score, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
+                uint32_t* __restrict__ masks, int wpr, float* __restrict__ segsum, float* __restrict__ segmax, int32_t* __restrict__ striptot, int n_strips)
 {
 	constexpr int K = R - 1, D = R + 2;
 	constexpr int HL = gc_halo_left(R), SW = gc_strip_width(R);
-	constexpr int SLOTS = 3 * D, RING = gc_ring_rows(R);
-	static_assert(RING == SLOTS + 2 * GC_OH, "ring = three slots and two mirrors");
+	constexpr int RB = gc_row_bytes(R), RING = gc_ring_rows(R);
 	constexpr float DIV = (float)(R * R);
 	constexpr float RCP = 1.0f / DIV;
 	extern __shared__ __align__(128) unsigned char gc_smem[];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	unsigned char* const ring = gc_smem + (size_t)warp * RING * GC_ROWBYTES + GC_OH * GC_ROWBYTES; /* slot 0 */
-	uint64_t* const bars = reinterpret_cast<uint64_t*>(gc_smem + (size_t)GC_WARPS * RING * GC_ROWBYTES) + 2 * warp;
+	unsigned char* const ring = gc_smem + (size_t)warp * RING * RB; /* physical slot 0 = the mirror; logical slot j = physical slot j + 1 */
+	uint64_t* const bars = reinterpret_cast<uint64_t*>(gc_smem + (size_t)GC_WARPS * RING * RB) + 2 * warp;
 	if (lane == 0) {
 		mbar_init(bars, 1);
 		mbar_init(bars + 1, 1);
@@ -196,13 +211,13 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	const size_t fbase = (size_t)f * w * h;
 	const uint32_t* flatf = flat + fbase;
 	const bool out_lane = c0 >= xs && c0 < xs + SW && c0 < w;
-	/* whole staged rows inside the image and 16-byte aligned: the TMA engine copies them; otherwise (strips at the left and
-	 * right image edge, widths that are not a multiple of 4) the lanes fill the ring themselves with clamped columns */
+	/* the 72 staged columns inside the image and rows 16-byte aligned: the TMA engine stages this strip; otherwise (strips at the
+	 * left and right image edge, widths that are not a multiple of 4) the lanes fill the ring themselves with clamped columns */
 	const bool bulk = xl >= 0 && xl + GC_NW <= w && (w & 3) == 0;
 	/* every column of the strip can take part in a window (1 <= c <= w-1): no per-column masks */
 	const bool cols_free = xs - HL >= 1 && xs - HL + 63 <= w - 1;
 	const bool ea = c0 >= 1 && c0 <= w - 1, eb = c0 + 1 >= 1 && c0 + 1 <= w - 1;
-	const uint32_t my = smem_u32(ring) + (uint32_t)(2 * lane + GC_OH) * 4u; /* shared address of column c0 in slot 0 */
+	const uint32_t my = smem_u32(ring) + (uint32_t)(2 * lane + GC_OH) * 4u; /* shared address of column c0 in physical slot 0, row 0 */
 	const int ecol[3] = { clampi(xl + lane, 0, w - 1), clampi(xl + lane + 32, 0, w - 1), clampi(xl + lane + 64, 0, w - 1) }; /* edge strips: CLAMP_TO_EDGE in x */
 	int nb = 0, ns = 0, npk = 0;
 	int32_t* rcf = rowcount + f * h;
@@ -219,45 +234,59 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
 	};
 
-	/* image rows first .. first+n-1 (n <= 32) into the ring slots p0, p0+1, ... (mod SLOTS), each also into the mirror of its
-	 * slot if it has one; rows outside the image repeat the edge row (CLAMP_TO_EDGE of gradientDot.cl:20 in y) */
-	auto stage_rows = [&](int first, int n, int p0, int stage) {
-		__syncwarp(); /* every lane has finished reading the slots that are overwritten */
-		int p = p0 + lane;
-		if (p >= SLOTS)
-			p -= SLOTS;
-		const int mirror = p < GC_OH ? SLOTS : (p >= SLOTS - GC_OH ? -SLOTS : 0);
+	/* image rows first .. first+D-1 into logical slot `slot` (and into the mirror if that is slot 2); `n` counts the staging
+	 * operations of this warp: operation n completes on mbarrier n & 1 */
+	auto stage_group = [&](int first, int slot, int n) {
+		__syncwarp(); /* every lane has finished reading the slot that is overwritten */
+		unsigned char* const dst = ring + (slot + 1) * (D * RB);
+		const bool twice = slot == 2;
 		if (bulk) {
-			const int n_mirrored = __popc(__ballot_sync(0xffffffffu, lane < n && mirror != 0));
-			if (lane == 0)
-				mbar_expect_tx(bars + stage, (uint32_t)(n + n_mirrored) * GC_ROWBYTES);
-			__syncwarp();
-			if (lane < n) {
-				const uint32_t* src = flatf + ((size_t)clampi(first + lane, 0, h - 1) * w + xl);
-				bulk_copy_g2s(ring + p * GC_ROWBYTES, src, GC_ROWBYTES, bars + stage);
-				if (mirror)
-					bulk_copy_g2s(ring + (p + mirror) * GC_ROWBYTES, src, GC_ROWBYTES, bars + stage);
+			uint64_t* bar = bars + (n & 1);
+			if (first >= 0 && first + D <= h) { /* the common case: one tensor copy, issued by one lane */
+				if (lane == 0) {
+					mbar_expect_tx(bar, (uint32_t)(twice ? 2 : 1) * D * RB);
+					tensor_copy_g2s(dst, &tmap, xl, first, f, bar);
+					if (twice)
+						tensor_copy_g2s(ring, &tmap, xl, first, f, bar);
+				}
+			} else { /* rows above the first / below the last image row repeat it: row by row with the row index clamped */
+				if (lane == 0)
+					mbar_expect_tx(bar, (uint32_t)(twice ? 2 : 1) * D * GC_NW * 4);
+				__syncwarp();
+				if (lane < D) {
+					const uint32_t* src = flatf + ((size_t)clampi(first + lane, 0, h - 1) * w + xl);
+					bulk_copy_g2s(dst + lane * RB, src, GC_NW * 4, bar);
+					if (twice)
+						bulk_copy_g2s(ring + lane * RB, src, GC_NW * 4, bar);
+				}
 			}
 		} else {
 			/* strips at the image edge (or rows that are not 16-byte aligned): 4-byte cp.async with clamped columns, three staged
 			 * words per lane and row; asynchronous like the bulk copies, completion through cp.async groups */
-			for (int i = 0; i < n; i++) {
-				const int pi = __shfl_sync(0xffffffffu, p, i), mi = __shfl_sync(0xffffffffu, mirror, i);
+#pragma unroll 2
+			for (int i = 0; i < D; i++) {
 				const uint32_t* src = flatf + (size_t)clampi(first + i, 0, h - 1) * w;
-				unsigned char* dst = ring + pi * GC_ROWBYTES + lane * 4;
+				unsigned char* d = dst + i * RB + lane * 4;
 #pragma unroll
 				for (int q = 0; q < 3; q++) {
 					if (q < 2 || lane < GC_NW - 64) {
-						cp_async4(dst + q * 128, src + ecol[q]);
-						if (mi)
-							cp_async4(dst + mi * GC_ROWBYTES + q * 128, src + ecol[q]);
+						cp_async4(d + q * 128, src + ecol[q]);
+						if (twice)
+							cp_async4(d - 3 * (D * RB) + q * 128, src + ecol[q]);
 					}
 				}
 			}
 			cp_async_commit();
 		}
 	};
-	(void)stage_rows;
+	auto wait_staged = [&](int n) {
+		if (bulk) {
+			mbar_wait(bars + (n & 1), (uint32_t)(n >> 1) & 1u);
+		} else {
+			cp_async_wait<0>();
+			__syncwarp();
+		}
+	};
 
 	float2 gq[D], hold[K > 0 ? K : 1], qa[D];
 #pragma unroll
@@ -279,8 +308,10 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	auto group = [&](auto FAST_C, int g, int slot) {
 		constexpr bool FAST = decltype(FAST_C)::value;
 		const int t = t0 + g * D;
-		const uint32_t ac = my + (uint32_t)(slot * D) * GC_ROWBYTES; /* tap addresses of step 0: centre row, then +-o rows / columns */
-		const uint32_t au = ac + (uint32_t)o * GC_ROWBYTES, ad = ac - (uint32_t)o * GC_ROWBYTES;
+		/* tap addresses of step 0: the slot starts with image row t+o (the tap below), the centre row is o rows and the tap above
+		 * 2o rows further down -- in the previous slot */
+		const uint32_t au = my + (uint32_t)((slot + 1) * D) * RB;
+		const uint32_t ac = au - (uint32_t)o * RB, ad = au - (uint32_t)(2 * o) * RB;
 		const uint32_t al = ac - (uint32_t)o * 4u, ar = ac + (uint32_t)o * 4u;
 #pragma unroll
 		for (int i = 0; i < K; i++)
@@ -295,14 +326,14 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		for (int s = 0; s < D; s++) {
 			const int tau = t + s;
 			/* gradientDot.cl:25-29: taps (x+-o, tau) and (x, tau+-o) of both columns */
-			const uint2 U = lds64a(au + s * GC_ROWBYTES), Dn = lds64a(ad + s * GC_ROWBYTES);
+			const uint2 U = lds64a(au + s * RB), Dn = lds64a(ad + s * RB);
 			uint2 Lf, Rt;
 			if constexpr (O_ODD) {
-				Lf = make_uint2(lds32a(al + s * GC_ROWBYTES), lds32a(al + s * GC_ROWBYTES + 4));
-				Rt = make_uint2(lds32a(ar + s * GC_ROWBYTES), lds32a(ar + s * GC_ROWBYTES + 4));
+				Lf = make_uint2(lds32a(al + s * RB), lds32a(al + s * RB + 4));
+				Rt = make_uint2(lds32a(ar + s * RB), lds32a(ar + s * RB + 4));
 			} else {
-				Lf = lds64a(al + s * GC_ROWBYTES);
-				Rt = lds64a(ar + s * GC_ROWBYTES);
+				Lf = lds64a(al + s * RB);
+				Rt = lds64a(ar + s * RB);
 			}
 			const int g0 = grad_dot_opaque(Rt.x, Lf.x, U.x, Dn.x), g1 = grad_dot_opaque(Rt.y, Lf.y, U.y, Dn.y);
 			const float2 gf = add2(make_float2(__int_as_float(g0 + 0x4B400000), __int_as_float(g1 + 0x4B400000)), make_float2(-12582912.0f, -12582912.0f));
@@ -387,21 +418,18 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		}
 	};
 
-	/* group g lives in slot g % 3: relative rows -o .. -1 of group 0 wrap to the top of the ring (and into the lower mirror) */
-	stage_rows(t0 - o, D + 2 * o, SLOTS - o, 0);
+	/* staging operation n brings the rows group n-1 adds; "group -1" are the D rows before t0+o, of which group 0 reads the last 2o */
+	stage_group(t0 + o - D, 2, 0);
+	stage_group(t0 + o, 0, 1);
+	wait_staged(0);
 	int slot = 0;
 #pragma unroll 1
 	for (int g = 0; g < n_groups; g++) {
 		const int t = t0 + g * D;
-		if (bulk) {
-			mbar_wait(bars + (g & 1), (uint32_t)(g >> 1) & 1u);
-		} else {
-			cp_async_wait<0>(); /* this group's rows (the next group's are issued below) */
-			__syncwarp();
-		}
+		wait_staged(g + 1);
 		const int next = slot == 2 ? 0 : slot + 1;
-		if (g + 1 < n_groups) /* the D rows the next group adds: its relative rows o .. D-1+o */
-			stage_rows(t + D + o, D, next * D + o, (g + 1) & 1);
+		if (g + 1 < n_groups)
+			stage_group(t + D + o, next, g + 2);
 		/* gradient rows t .. t+D-1 and output rows t-R .. t-R+D-1 all inside [ys, ye) (hence inside [1, h-1]) */
 		if (cols_free && t - R >= ys && t + D <= ye)
 			group(IntC<1>{}, g, slot);

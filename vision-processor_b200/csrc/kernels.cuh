@@ -2361,27 +2361,47 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 	__syncthreads();
 	const size_t fbase = (size_t)f * w * h;
 	uint8_t* out = matches + (size_t)f * match_frame_stride;
-	for (int t = warp; t < rows_per_cta; t += 8) {
-		if (s_cnt[t] == 0)
-			continue;
+	/* The CTA's blobs are dealt out to its warps one by one, in rank order (blob i of the CTA -> warp i % 8): the blobs of a
+	 * robot share a few rows, and a warp per ROW would leave most warps idle behind the one that owns those rows.  A warp
+	 * finds its blob from the counts: the row by a vote over s_pre, the pixel as the n-th set bit of the row's mask words. */
+	const int first = s_pre[0], last_t = rows_per_cta - 1;
+	const int n_here = s_pre[last_t] + s_cnt[last_t] - first;
+	for (int i = warp; i < n_here && first + i < max_matches; i += 8) {
+		const int rank = first + i;
+		int t = 0;
+		for (int t0 = 0; t0 < rows_per_cta; t0 += 32) { /* the row whose rank range holds `rank` */
+			const int tt = t0 + lane;
+			const bool hit = tt < rows_per_cta && s_cnt[tt] > 0 && rank >= s_pre[tt] && rank < s_pre[tt] + s_cnt[tt];
+			const unsigned v = __ballot_sync(0xffffffffu, hit);
+			if (v)
+				t = t0 + __ffs(v) - 1;
+		}
 		const int y = row0 + t;
-		int rank = s_pre[t];
+		int n = rank - s_pre[t]; /* n-th blob of the row, counted from the left */
 		const uint32_t* mk = masks + ((size_t)f * h + y) * wpr;
-		for (int base = 0; base < wpr && rank < max_matches; base += 32) {
+		int x = -1;
+		for (int base = 0; base < wpr && x < 0; base += 32) {
 			const uint32_t mine = base + lane < wpr ? mk[base + lane] : 0u;
-			unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
-			while (nz && rank < max_matches) {
-				const int src = __ffs(nz) - 1;
-				nz &= nz - 1;
-				uint32_t word = __shfl_sync(0xffffffffu, mine, src);
-				while (word && rank < max_matches) {
-					const int b = __ffs(word) - 1;
-					word &= word - 1;
-					emit_match(img + fbase, circ + fbase, w, h, (base + src) * 32 + b, y, radius, out + 22 * (size_t)rank, lane);
-					rank++;
-				}
+			const int c = __popc(mine);
+			int incl = c;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int u = __shfl_up_sync(0xffffffffu, incl, d);
+				if (lane >= d)
+					incl += u;
+			}
+			const int total = __shfl_sync(0xffffffffu, incl, 31);
+			if (n < total) {
+				const unsigned v = __ballot_sync(0xffffffffu, n < incl); /* first lane whose inclusive count exceeds n */
+				const int src = __ffs(v) - 1;
+				const uint32_t word = __shfl_sync(0xffffffffu, mine, src);
+				const int skip = n - (__shfl_sync(0xffffffffu, incl, src) - __shfl_sync(0xffffffffu, c, src));
+				x = (base + src) * 32 + (int)__fns(word, 0, skip + 1);
+			} else {
+				n -= total;
 			}
 		}
+		emit_match(img + fbase, circ + fbase, w, h, x, y, radius, out + 22 * (size_t)rank, lane);
 	}
 }
 
