@@ -804,16 +804,35 @@ constexpr int HOIST4_STAGES = VP_HOIST4_STAGES;
 constexpr int HOIST4_TBUF = VP_HOIST4_TBUF;
 constexpr size_t HOIST4_SMEM = HOIST4_TBUF * (size_t)HT * 4 + HOIST4_STAGES * 4 * (size_t)HRING;
 
-/* w * (byte LO, byte LO+1) of a staged word as ONE packed FMA on the biased floats 2^23 + b (0x4B0000bb):
- * fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once, i.e. bit for bit mul.rn(w, float(b)); wm = -w * 2^23
- * is exact (a power-of-two scaling) */
+/* build-time A/B: how a staged byte becomes a product.
+ * 1 (default): the byte is used as the fp32 DENORMAL b * 2^-149 (one PRMT against zero) and the weight carries a factor 2^100
+ *    (folded into the x-axis values once per tile): mul.rn(w * 2^100, b * 2^-149) = RN(w * b) * 2^-49 exactly -- scaling by a
+ *    power of two commutes with the rounding as long as nothing leaves the normal range, and the smallest non-zero product is
+ *    2^-48 * 2^-49.  Every sum and the final 2^23 * 2^-49 rounding add carry the same factor, so the mantissa bits -- the rounded
+ *    integer -- are those of the canonical arithmetic, under another exponent: the "bias" of the integer tail is 0x32800000
+ *    instead of 0x4B000000.  Blackwell multiplies denormal operands at full rate (tools/ubench/pipes.cu).  Against variant 0
+ *    this removes one FMUL per tap and quad of frames (w * -2^23) and turns the products from 3-operand FFMA2 into FMUL2.
+ * 0: the byte is OR-ed under the exponent of 2^23 and fma(2^23 + b, w, -w * 2^23) gives the product. */
+#ifndef VP_HOIST4_DENORM
+#define VP_HOIST4_DENORM 1
+#endif
+constexpr float HOIST4_WSCALE = VP_HOIST4_DENORM ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
+constexpr float HOIST4_ROUND = VP_HOIST4_DENORM ? 1.4901161193847656e-08f /* 2^23 * 2^-49 = 2^-26 */ : 8388608.0f;
+
+/* w * (byte LO, byte LO+1) of a staged word, two frames at once; bit for bit mul.rn(w, float(b)) (times 2^-49 in variant 1) */
 template <int LO>
 __device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w, float wm)
 {
+#if VP_HOIST4_DENORM
+	(void)wm;
+	return mul2(make_float2(__uint_as_float(__byte_perm(wd, 0u, 0x4440 + LO)), __uint_as_float(__byte_perm(wd, 0u, 0x4441 + LO))), make_float2(w, w));
+#else
+	/* fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once; wm = -w * 2^23 is exact (a power-of-two scaling) */
 	const float2 b = make_float2(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7440 + LO)), __uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7441 + LO)));
 	unsigned long long r;
 	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(b)), "l"(f2_bits(make_float2(w, w))), "l"(f2_bits(make_float2(wm, wm))));
 	return bits_f2(r);
+#endif
 }
 
 template <int FMT, bool FULL>
@@ -841,15 +860,19 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 				const float2 wp = W[k][4 * (c >> 1) + tap];
 				const float w = (c & 1) ? wp.y : wp.x;
 #endif
+#if VP_HOIST4_DENORM
+				const float wm = 0.0f;
+#else
 				const float wm = __fmul_rn(w, -8388608.0f);
+#endif
 				const float2 pab = weighted_pair<0>(wd, w, wm);
 				const float2 pcd = weighted_pair<2>(wd, w, wm);
 				/* ((p00 + p10) + p01) + p11, every sum rounded on its own */
 				ab[c] = tap == 0 ? pab : add2_opaque(pab, ab[c], one2);
 				cd[c] = tap == 0 ? pcd : add2_opaque(pcd, cd[c], one2);
 			}
-			ab[c] = add2(ab[c], make_float2(8388608.0f, 8388608.0f)); /* RNE to integer in the mantissa */
-			cd[c] = add2(cd[c], make_float2(8388608.0f, 8388608.0f));
+			ab[c] = add2(ab[c], make_float2(HOIST4_ROUND, HOIST4_ROUND)); /* RNE to integer in the mantissa */
+			cd[c] = add2(cd[c], make_float2(HOIST4_ROUND, HOIST4_ROUND));
 		}
 		uint32_t* o = out + (uint32_t)(4 * k) * (uint32_t)wf;
 		const bool in = FULL || (okx && 4 * k < rows_ok);
@@ -1027,6 +1050,9 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 		axis_staged2(add2(make_float2(pos[k].y, pos[k].y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
 		const float2 ayp = make_float2(ay.x, ay.x), oyp = make_float2(oy.x, oy.x);
 		const float2 ayn = make_float2(ay.y, ay.y), oyn = make_float2(oy.y, oy.y);
+		/* variant VP_HOIST4_DENORM: the factor 2^100 of the weights rides on the x-axis values (exact: a power of two) */
+		ox = mul2(ox, make_float2(HOIST4_WSCALE, HOIST4_WSCALE));
+		ax = mul2(ax, make_float2(HOIST4_WSCALE, HOIST4_WSCALE));
 #if VP_HOIST4_AXES
 		W[k][0] = ox; W[k][1] = ax; W[k][2] = oy; W[k][3] = ay; /* oy = (oyp, oyn), ay = (ayp, ayn) */
 		(void)oyp; (void)ayp; (void)oyn; (void)ayn;
