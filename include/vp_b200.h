@@ -275,6 +275,32 @@ VP_API int vp_f2nv12_batch_device(vp_ctx* ctx, const float* d_f32, int n_frames,
 VP_API int vp_raw2nv12_batch_device(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, int fmt, int wq, int hq, uint8_t* d_nv12, size_t nv12_stride,
                                     int sample_mode);
 
+/* ---- NV12 hand-off to a hardware encoder -------------------------------------------------------------
+ * What the reference's encoder thread does with a debug view (src/rtpstreamer.cpp:120-121, 177-181): it maps the NV12
+ * RawImage and points libav at it with data[0] = buffer, data[1] = buffer + W*H and linesize[0] = linesize[1] = W; the
+ * codec is h264_nvenc when available (rtpstreamer.cpp:62).  The batched conversions above leave exactly that layout in
+ * DEVICE memory, one surface per frame, so an NVENC session (or libav with a CUDA hw frame) can take the planes without the
+ * 1.9 MB device->host->device round trip per view; this descriptor states the contract instead of leaving it to pointer
+ * arithmetic at the call site:
+ *   y            luma plane: `height` rows of `width` bytes at pitch_y = width (dense, as libav's linesize expects)
+ *   uv           chroma plane at y + width*height: height/2 rows of interleaved (U, V) byte pairs at pitch_uv = width
+ *   width,height both even (Perspective.cpp:118-122 rounds the flat size up to even "for rtpstreamer"; quads are even by construction)
+ *   bytes_used   width*height*3/2; the reference allocates width*height*2 per buffer (opencl.cpp:27, :132)
+ *   aligned16    1 when y, uv and both pitches are multiples of 16 bytes (what NVENC's registered CUDA resources and
+ *                cuMemcpy2D-style consumers want); true for every frame of a batch when width % 16 == 0 and
+ *                nv12_stride % 16 == 0 and the base comes from cudaMalloc / vp_buf_alloc */
+typedef struct {
+	uint8_t* y;
+	uint8_t* uv;
+	int32_t width, height;
+	int32_t pitch_y, pitch_uv;
+	size_t bytes_used;
+	int32_t aligned16;
+} vp_nv12_surface;
+/* surface of frame `frame` of a batch written by vp_*2nv12_batch_device(..., d_nv12, nv12_stride) (frame 0, any stride, for the
+ * single-view calls).  Pure arithmetic, no device access; VP_ERR_INVALID for odd sizes or a stride below 1.5*w*h. */
+VP_API int vp_nv12_surface_of(uint8_t* d_nv12, int w, int h, size_t nv12_stride, int frame, vp_nv12_surface* out);
+
 /* blocking copies ordered after everything enqueued on the context stream (tests, tools) */
 VP_API int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes);
 VP_API int vp_copy_to_device(vp_ctx* ctx, void* dev, const void* host, size_t bytes);

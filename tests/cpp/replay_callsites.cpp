@@ -14,6 +14,8 @@
  *   rtpstreamer.cpp:177-181    the encoder thread maps an NV12 RawImage it holds a shared_ptr to
  *   blob_benchmark.cpp:162,190-191  read map of blobCenter, nth_element in place over rowPitch*height
  *   opencvdriver.cpp:57-66 / mvimpactdriver.cpp:24  frame written through a map / copy-in constructor
+ *   cameradriver.h:35-47 / main.cpp:262-267   frames pulled through CameraDriver::readImage() until it returns nullptr
+ *                                             (include/compat/syntheticdriver.h: the synthetic Bayer driver of SURVEY 8 f4)
  *
  * usage: replay_callsites <in.bin> <out.bin>     in.bin = vp_params + raw frame
  */
@@ -25,6 +27,7 @@
 
 #include "opencl.h"
 #include "cl_kernels.h"
+#include "syntheticdriver.h"
 
 typedef struct __attribute__((packed)) { /* Perspective.h:22-29 */
 	int shape[2];
@@ -148,10 +151,20 @@ int main(int argc, char** argv) {
 	FILE* out = fopen(argv[2], "wb");
 	if (!out) FATAL("cannot open " << argv[2]);
 
+	/* the camera: two copies of the frame behind the CameraDriver interface */
+	std::vector<unsigned char> two(frame.begin(), frame.end());
+	two.insert(two.end(), frame.begin(), frame.end());
+	std::unique_ptr<CameraDriver> camera = std::make_unique<SyntheticDriver>(std::move(two), r.cameraFormat, p.wq, p.hq, 60.0);
+	if (camera->format().pixelSize() != r.cameraFormat->pixelSize() || camera->expectedFrametime() <= 0.0) FATAL("driver format");
+
 	for (int frameId = 1; frameId <= 3; frameId++) { /* three frames: pooled images are reused (use_count()==1) */
-		/* frame 1: the OpenCV driver writes into a mapped buffer; frame 2: copy-in constructor; frame 3: map again */
+		/* frame 1: pulled from the camera driver like main.cpp:262-267; frame 2: copy-in constructor; frame 3: the OpenCV driver's
+		 * way, written into a mapped buffer */
 		std::shared_ptr<RawImage> img;
-		if (frameId == 2) {
+		if (frameId == 1) {
+			img = camera->readImage();
+			if (!img || img->width != p.wq || img->height != p.hq || img->timestamp != camera->getTime()) FATAL("driver frame");
+		} else if (frameId == 2) {
 			img = std::make_shared<RawImage>(r.cameraFormat, p.wq, p.hq, (double)frameId, frame.data());
 		} else {
 			img = std::make_shared<RawImage>(r.cameraFormat, p.wq, p.hq, (double)frameId);
@@ -218,6 +231,7 @@ int main(int argc, char** argv) {
 			r.openCl->printRuntimes(); /* main.cpp:363-366 (BENCHMARK) */
 		r.openCl->clearEvents(); /* main.cpp:372 */
 	}
+	if (!camera->readImage() || camera->readImage()) FATAL("the driver must hand out its second frame and then end the stream");
 	fclose(out);
 	LOG("replay ok");
 	return 0;

@@ -63,3 +63,19 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(root, f)).read()
                 assert "vp_oracle" not in text and "import oracle" not in text and "libvp_clref" not in text, f
+
+
+def test_nv12_surface_contract():
+    """the layout an encoder session takes from the batched NV12 conversions -- src/rtpstreamer.cpp:120-121
+    (linesize = W for both planes, chroma at +W*H) -- stated by vp_nv12_surface_of; pure arithmetic, no GPU."""
+    import ctypes as C
+    from vpb200 import lib
+    L = lib.load()
+    s = lib.Nv12Surface()
+    base, w, h, stride = 0x7f0000000000, 1224, 1024, 2 * 1224 * 1024
+    assert L.vp_nv12_surface_of(C.c_void_p(base), w, h, stride, 3, C.byref(s)) == 0
+    assert s.y == base + 3 * stride and s.uv == s.y + w * h and (s.pitch_y, s.pitch_uv) == (w, w)
+    assert (s.width, s.height, s.bytes_used) == (w, h, w * h * 3 // 2) and s.aligned16 == 0   # 1224 is not a multiple of 16
+    assert L.vp_nv12_surface_of(C.c_void_p(base), 2048, 1500, 2 * 2048 * 1500, 1, C.byref(s)) == 0 and s.aligned16 == 1
+    assert L.vp_nv12_surface_of(C.c_void_p(base), 1223, 1024, stride, 0, C.byref(s)) == 1        # odd width: VP_ERR_INVALID
+    assert L.vp_nv12_surface_of(C.c_void_p(base), w, h, w * h, 1, C.byref(s)) == 1               # stride below a frame

@@ -1,0 +1,34 @@
+"""SURVEY 8 row g on the GPU: the CUDA library's `blobCenter` image of the headline scene scored against the rendered ground
+truth exactly like the reference's blob_benchmark does (blob_benchmark.cpp:45-111,160-222).  Independent of the oracle."""
+import time
+
+import numpy as np
+import pytest
+
+import common
+from test_blob_benchmark import check, scene
+from vpb200 import blob_benchmark as BB
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("k2,tilt", [(0.0, 0.0), (0.12, 0.0), (0.12, 0.2)])
+def test_detected_peaks_land_on_the_rendered_blobs(ctx, k2, tilt):
+    persp, lp, sc, raw = scene(k2, tilt)
+    vp = common.to_vp(common.to_vpo(lp))
+    ctx.detect(raw, vp)
+    t0 = time.perf_counter()
+    got = ctx.detect(raw, vp)
+    dt = time.perf_counter() - t0
+    acc = BB.Accumulators()
+    BB.score_frame(acc, persp, got["circ"], sc, processing_time=dt)
+    res = BB.summary(acc, persp)
+    check(res, 16 * 5 + 4, persp.field_scale)
+    print(res["lines"][0])
+    print(res["lines"][1])
+    # every ground-truth blob is also in the blob LIST the library returns, within a pixel of where the benchmark finds it
+    m = got["matches"][0]
+    for (x, y, z, rad, rgb) in sc.blobs():
+        f = BB.field2flat(persp, (x, y, z if rad != sc.field.ball_radius else 30.0), 180.0)
+        d = np.hypot(m["x"] - f[0], m["y"] - f[1])
+        assert np.nanmin(d) < 1.5

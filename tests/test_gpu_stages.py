@@ -214,6 +214,31 @@ def test_batched_nv12_views_match_the_per_frame_calls(ctx, port):
         ctx.nv12_batch("rgba", rgba, w, h, stride=used - 2)              # stride smaller than a frame
 
 
+def test_batched_nv12_surfaces_are_what_an_encoder_reads(ctx, port):
+    """the planes vp_nv12_surface_of describes for frame i of a batch ARE frame i's luma and chroma --
+    read the way the reference's encoder thread reads them (rtpstreamer.cpp:120-121,177-181: rows of `pitch` bytes from `y`,
+    height/2 rows of interleaved U,V from `uv`) -- and they never leave the device."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    n, w, h = 4, 64, 48
+    rgba = rng.integers(0, 256, (n, h, w, 4), dtype=np.uint8)
+    stride = 2 * w * h
+    src = ctx.buffer(rgba.nbytes, rgba.reshape(-1))
+    dst = ctx.buffer(n * stride)
+    ctx._ck(ctx.lib.vp_rgba2nv12_batch_device(ctx.h, C.c_void_p(src.device_ptr), n, w, h, C.c_void_p(dst.device_ptr), stride))
+    for i in range(n):
+        s = lib.Nv12Surface()
+        ctx._ck(ctx.lib.vp_nv12_surface_of(C.c_void_p(dst.device_ptr), w, h, stride, i, C.byref(s)))
+        assert s.aligned16 == 1 and s.pitch_y == w and s.pitch_uv == w
+        y = ctx.to_host(s.y, s.pitch_y * h).reshape(h, s.pitch_y)[:, :w]
+        uv = ctx.to_host(s.uv, s.pitch_uv * h // 2).reshape(h // 2, s.pitch_uv)[:, :w]
+        want = port.rgba2nv12(rgba[i])
+        np.testing.assert_array_equal(y.reshape(-1), want[: w * h])
+        np.testing.assert_array_equal(uv.reshape(-1), want[w * h: w * h * 3 // 2])
+    src.release()
+    dst.release()
+
+
 @pytest.mark.parametrize("fmt", [0, 1])
 def test_wide_nv12_kernels_on_random_bytes(ctx, port, fmt):
     """The 8x2-pixels-per-thread kernels (w % 8 == 0, aligned views): uniformly random bytes hit every rounding case of the

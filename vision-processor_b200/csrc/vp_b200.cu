@@ -2301,6 +2301,23 @@ int vp_detect_images(vp_ctx* ctx, const uint8_t** d_flat, const float** d_grad, 
 	return VP_OK;
 }
 
+int vp_nv12_surface_of(uint8_t* d_nv12, int w, int h, size_t nv12_stride, int frame, vp_nv12_surface* out)
+{
+	if (!d_nv12 || !out || w <= 0 || h <= 0 || (w & 1) || (h & 1) || frame < 0)
+		return fail(nullptr, VP_ERR_INVALID, "NV12 surface: null pointer, negative frame or odd size %dx%d", w, h);
+	const size_t used = (size_t)w * h * 3 / 2;
+	if (frame > 0 && nv12_stride < used)
+		return fail(nullptr, VP_ERR_INVALID, "NV12 surface: stride %zu is smaller than a frame (%zu bytes)", nv12_stride, used);
+	out->y = d_nv12 + (size_t)frame * nv12_stride;
+	out->uv = out->y + (size_t)w * h; /* rtpstreamer.cpp:121: data[1] = buffer + width*height */
+	out->width = w;
+	out->height = h;
+	out->pitch_y = out->pitch_uv = w; /* rtpstreamer.cpp:120: linesize = width for both planes */
+	out->bytes_used = used;
+	out->aligned16 = (((uintptr_t)out->y | (uintptr_t)out->uv | (uintptr_t)w) & 15u) == 0;
+	return VP_OK;
+}
+
 int vp_copy_to_host(vp_ctx* ctx, void* host, const void* dev, size_t bytes)
 {
 	REQUIRE(ctx, ctx && (bytes == 0 || (host && dev)), "null argument");

@@ -84,6 +84,12 @@ class FieldSizeC(C.Structure):
                 ("boundary_width_goal_line", C.c_float), ("ball_radius", C.c_float)]
 
 
+class Nv12Surface(C.Structure):
+    """vp_nv12_surface: the layout an encoder session consumes (src/rtpstreamer.cpp:120-121)."""
+    _fields_ = [("y", C.c_void_p), ("uv", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("pitch_y", C.c_int32), ("pitch_uv", C.c_int32),
+                ("bytes_used", C.c_size_t), ("aligned16", C.c_int32)]
+
+
 class Geometry(C.Structure):
     """vp_geometry: what Perspective::geometryCheck leaves behind (src/Perspective.h:32-58)."""
     _fields_ = [("model", CameraModel), ("field_scale", C.c_float), ("visible_field_extent", C.c_float * 4),
@@ -208,6 +214,7 @@ def load() -> C.CDLL:
         "vp_f2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t]),
         "vp_raw2nv12_batch_device": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.c_int]),
         "vp_blobs_to_field_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp, vp]),
+        "vp_nv12_surface_of": (C.c_int, [vp, C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(Nv12Surface)]),
         "vp_copy_to_host": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_copy_to_device": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "vp_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(vp)]),

@@ -66,6 +66,23 @@ class Scene:
                                             "orientation": float(r.orientation), "height": float(r.height)})
         return out
 
+    def detection_frame(self, model: CameraModel, camera_id: int = 0, frame_number: int = 1, t_capture: float = 0.0) -> dict:
+        """One SSL_DetectionFrame with every field src/GroundTruth.cpp:23-78 reads (the decoders call .as<> on confidence,
+        x, y, pixel_x, pixel_y without a default, so those must be present): pixel positions through the camera model."""
+        def px(x, y, z):
+            p = model.field2image(np.array([x, y, z], F32))
+            return float(p[0]), float(p[1])
+        frame = {"camera_id": int(camera_id), "frame_number": int(frame_number), "t_capture": float(t_capture), "t_sent": float(t_capture),
+                 "balls": [], "robots_blue": [], "robots_yellow": []}
+        for b in self.balls:
+            u, v = px(b.x, b.y, b.z)
+            frame["balls"].append({"confidence": 1.0, "x": float(b.x), "y": float(b.y), "z": float(b.z), "pixel_x": u, "pixel_y": v})
+        for r in self.robots:
+            u, v = px(r.x, r.y, r.height)
+            frame["robots_" + r.team].append({"confidence": 1.0, "robot_id": int(r.robot_id), "x": float(r.x), "y": float(r.y),
+                                              "orientation": float(r.orientation), "pixel_x": u, "pixel_y": v, "height": float(r.height)})
+        return frame
+
     def blobs(self) -> list:
         """(x, y, z, radius_mm, rgb) of every coloured disc, robots first (scoreBot, blob_benchmark.cpp:86-111)."""
         out = []
@@ -205,3 +222,28 @@ def noise_frame(sensor_w: int, sensor_h: int, seed: int, fmt: int = FMT_RGGB) ->
     rng = np.random.default_rng(seed)
     shape = (sensor_h, sensor_w, 3) if fmt == FMT_BGR else (sensor_h, sensor_w)
     return rng.integers(0, 256, shape, dtype=np.uint8)
+
+
+def write_ground_truth_yaml(path: str, frames: list) -> None:
+    """`frames` (Scene.detection_frame dicts) as the YAML sequence parseGroundTruth loads (src/GroundTruth.cpp:81-83:
+    YAML::LoadFile(source).as<std::vector<SSL_DetectionFrame>>()).  Plain block style, no anchors."""
+    import yaml
+    with open(path, "w") as f:
+        yaml.safe_dump(frames, f, default_flow_style=False, sort_keys=False)
+
+
+def parse_ground_truth_yaml(path: str) -> list:
+    """What src/GroundTruth.cpp:23-78 extracts, with its required/optional split (a missing required key raises like
+    yaml-cpp's .as<> would); used to check that what write_ground_truth_yaml emits is what the reference reads."""
+    import yaml
+    out = []
+    for node in yaml.safe_load(open(path)):
+        fr = {k: node[k] for k in ("camera_id", "frame_number", "t_capture", "t_sent")}
+        if "t_capture_camera" in node:
+            fr["t_capture_camera"] = node["t_capture_camera"]
+        fr["balls"] = [dict({k: b[k] for k in ("confidence", "x", "y", "pixel_x", "pixel_y")}, **{k: b[k] for k in ("area", "z") if k in b}) for b in node["balls"]]
+        for team in ("robots_blue", "robots_yellow"):
+            fr[team] = [dict({k: r[k] for k in ("confidence", "x", "y", "pixel_x", "pixel_y")}, **{k: r[k] for k in ("robot_id", "orientation", "height") if k in r})
+                        for r in node[team]]
+        out.append(fr)
+    return out
