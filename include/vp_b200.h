@@ -317,9 +317,9 @@ VP_API int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group);
 /* tuning knob: number of CUDA streams the frame groups of one batch are spread over (1..4, default 3) so that the
  * issue-bound reprojection of one group overlaps the bandwidth-bound scans of another */
 VP_API int vp_ctx_set_lanes(vp_ctx* ctx, int lanes);
-/* A/B switch, results are bit-identical: 0 = direct-gather reprojection, 1 = shared-memory staged kernel (weights
- * derived per frame), 2 (default) = staged kernel that keeps the frame-invariant weights of a tile in registers over a
- * chunk of frames of the batch */
+/* A/B switch, results are bit-identical: 0 = direct-gather reprojection, 1 or 2 (default) = shared-memory staged kernels that
+ * keep the frame-invariant weights of a tile in registers over a chunk of frames of the batch (four frames per shared-memory
+ * word for chunks of at least four frames) */
 VP_API int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on);
 /* tuning knob of variant 2: frames of a launch group one CTA processes with the same registers (0 = automatic: 32, fewer
  * when the grid would not fill the GPU) */
@@ -336,27 +336,16 @@ VP_API int vp_ctx_set_strips(vp_ctx* ctx, int strips);
 VP_API int vp_ctx_set_latency_graph(vp_ctx* ctx, int on);
 /* one-frame calls of vp_detect_host served by a graph replay so far (tests, tools) */
 VP_API uint64_t vp_latency_graph_replays(const vp_ctx* ctx);
-/* A/B switch (default on; needs sat_free on, circle radius 1..12, gradient offset <= 4): gradientDot, the box sums of
+/* A/B switch (default on; circle radius 1..12, gradient offset <= 4 and <= (radius+2)/2): gradientDot, the box sums of
  * satBlobCenter, circularity and peak classification in ONE kernel that reads the flat image once (no row sums, no SAT) vs
  * gradient + row prefix sums followed by the streaming circularity kernel; results are bit-identical */
 VP_API int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on);
-/* A/B switch (default on): circularity + peak classification by the register-streaming kernel vs the shared-memory
- * tiled kernel; results are bit-identical */
-VP_API int vp_ctx_set_stream_circ(vp_ctx* ctx, int on);
-/* A/B switch (default on; needs stream_circ on and fused_sat off): circularity straight from the row prefix sums -- no
- * column scan, no materialised summed-area table; the exactness bound of the SAT is checked after the fact and frames
- * that leave it are redone in the reference's sequential order; results are bit-identical */
-VP_API int vp_ctx_set_sat_free(vp_ctx* ctx, int on);
-/* A/B switch (default OFF: measured 6.8 vs 5.8 us/frame on B200): gradient + summed-area table in one pass (strip-resident in shared memory, aggregate
- * look-back between strips) vs gradient+row scan followed by a column scan; results are bit-identical */
-VP_API int vp_ctx_set_fused_sat(vp_ctx* ctx, int on);
-
 /* what the most recent fused call (vp_detect_batch_device / vp_detect_host) actually launched, for tests and sweeps that
  * must know which specialised kernel they exercised: plan[0] reprojection kernel (0 direct gather, 1 staged per frame,
  * 2 frame-invariant one frame per word, 4 frame-invariant four frames per word), plan[1] frames per CTA of that kernel,
- * plan[2] frames per launch group, plan[3] streams used, plan[4] circularity path (0 unfused generic radius, 1 tiled from
- * the SAT, 2 streaming from the SAT, 3 streaming from row sums, 4 fused gradient + circularity), plan[5] rows per
- * circularity segment, plan[6] 1 when the reprojection staged its tiles with TMA, plan[7] reserved */
+ * plan[2] frames per launch group, plan[3] streams used, plan[4] circularity flow (0 materialised SAT + unfused circle for
+ * radii outside 1..12, 3 row sums + streaming circularity, 4 fused gradient + circularity), plan[5] rows per
+ * circularity segment, plan[6], plan[7] reserved */
 VP_API int vp_detect_last_plan(const vp_ctx* ctx, int32_t plan[8]);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */

@@ -55,13 +55,8 @@ def test_detect_unusual_geometry(ctx, port, scale_mul, dx, dy):
     try:
         direct = ctx.detect(raw, common.to_vp(p))
     finally:
-        ctx.set_staged_reproject(1)  # staged, per-frame weights
-        try:
-            staged = ctx.detect(raw, common.to_vp(p))
-        finally:
-            ctx.set_staged_reproject(2)
+        ctx.set_staged_reproject(2)
     np.testing.assert_array_equal(direct["flat"], want["flat"])
-    np.testing.assert_array_equal(staged["flat"], want["flat"])
 
 
 def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
@@ -74,17 +69,16 @@ def test_detect_degenerate_camera_gives_nonfinite_coordinates(ctx, port):
     check_frame(got, 0, want)
 
 
-@pytest.mark.parametrize("switch", ["staged_reproject", "stream_circ", "fused_sat", "sat_free", "fused_gradcirc"])
+@pytest.mark.parametrize("switch", ["staged_reproject", "fused_gradcirc"])
 @pytest.mark.parametrize("kw", [dict(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.3, n_robots=4, n_balls=3, seed=7), dict(wq=102, hq=66, fmt=1, k2=0.12, tilt=0.2),
                                 dict(wq=160, hq=120, fmt=0, frame="noise", seed=3, max_blobs=64)])
 def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
-    """Every A/B switch selects a different kernel for the same stage (direct-gather vs staged vs frame-invariant-hoisted reprojection, tiled vs
-    streaming circularity, two-pass vs single-pass SAT, circularity from a materialised SAT vs straight from the row sums): all settings must give the oracle's bits."""
+    """Every A/B switch selects a different kernel for the same stage (direct-gather vs frame-invariant-hoisted reprojection; gradient + row
+    sums + streaming circularity vs the fused gradient + circularity kernel): all settings must give the oracle's bits."""
     p, raw, _ = common.make_case(**kw)
     want = port.detect(raw, p)
     setter = getattr(ctx, "set_" + switch)
-    values = {"staged_reproject": (0, 1, 2), "stream_circ": (False, True), "fused_sat": (True, False), "sat_free": (False, True),
-              "fused_gradcirc": (False, True)}[switch]  # default last
+    values = {"staged_reproject": (0, 2), "fused_gradcirc": (False, True)}[switch]  # default last
     default = values[-1]
     try:
         for value in values:
@@ -99,29 +93,28 @@ def test_alternative_kernels_agree_with_the_oracle(ctx, port, kw, switch):
         setter(default)
 
 
-def test_sat_fallback_through_every_kernel_variant(ctx, port):
-    """The >2^22 fallback (sequential-order SAT, literal 16-tap circularity) through the tiled and the single-pass variants."""
+def test_sat_fallback_through_every_flow(ctx, port):
+    """The >2^22 fallback (sequential-order SAT, literal 16-tap circularity) behind the fused gradient + circularity kernel, behind the
+    row-sum flow, and -- radius 13 -- on the materialised-SAT path of radii outside the specialised range."""
     p, _, _ = common.make_case(wq=256, hq=256, scale_mm=4.0)
     h, w = 2 * p.hq, 2 * p.wq
     yy, xx = np.mgrid[0:h, 0:w]
     raw = (((xx + yy) // 6) % 2 * 255).astype(np.uint8).reshape(-1)
     want = port.detect(raw, p)
     try:
-        for stream_circ, fused_sat, sat_free, gc in [(False, False, True, True), (True, True, True, True), (False, True, True, True), (True, False, False, True),
-                                                     (True, False, True, False), (True, False, True, True)]:
-            ctx.set_stream_circ(stream_circ)
-            ctx.set_fused_sat(fused_sat)
-            ctx.set_sat_free(sat_free)
+        for gc in (False, True):
             ctx.set_fused_gradcirc(gc)
             got = ctx.detect(raw, common.to_vp(p))
             assert got["sat_fallbacks"] == 1
             common.assert_float_images_equal(got["circ"], want["circ"])
             check_frame(got, 0, want)
     finally:
-        ctx.set_stream_circ(True)
-        ctx.set_fused_sat(False)
-        ctx.set_sat_free(True)
         ctx.set_fused_gradcirc(True)
+    p.circle_radius = 13
+    want = port.detect(raw, p)
+    got = common.detect_device(ctx, [raw, raw], common.to_vp(p), images=("circ",))
+    assert got["plan"]["circ"] == 0 and got["sat_fallbacks"] == 2
+    common.assert_frame_equal(got, 1, want, images=("circ",))
 
 
 def test_detect_batch_of_distinct_frames(ctx, port):
@@ -297,8 +290,8 @@ def test_sat_beyond_2p24_falls_back_to_sequential_order(ctx, port):
     check_frame(got, 0, want)
 
 
-@pytest.mark.parametrize("sat_free,gc", [(True, True), (True, False), (False, False)])
-def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free, gc):
+@pytest.mark.parametrize("gc", [True, False])
+def test_flagged_and_clean_frames_in_one_batch(ctx, port, gc):
     """Frames that leave the exactness bound -- one through its row sums (wide stripes), one only through the summed-area
     table (found after the fast pass when there is no SAT) -- between clean frames of the same batch: the flagged ones
     are redone in sequential order, the clean ones keep the results of the fast pass."""
@@ -318,7 +311,6 @@ def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free, gc):
     n, nf, rb = len(frames), p.wf * p.hf, frames[0].size
     bufs = dict(raw=ctx.buffer(n * rb, np.stack(frames)), flat=ctx.buffer(n * nf * 4), grad=ctx.buffer(n * nf * 4), circ=ctx.buffer(n * nf * 4),
                 m=ctx.buffer(n * vp.max_blobs * 22), c=ctx.buffer(n * 12))
-    ctx.set_sat_free(sat_free)
     ctx.set_fused_gradcirc(gc)
     try:
         ctx.detect_batch_device(bufs["raw"].device_ptr, n, vp, bufs["flat"].device_ptr, bufs["grad"].device_ptr, bufs["circ"].device_ptr,
@@ -328,7 +320,6 @@ def test_flagged_and_clean_frames_in_one_batch(ctx, port, sat_free, gc):
         counter = bufs["c"].read(np.int32).reshape(n, 3)
         m = bufs["m"].read(np.uint8).reshape(n, vp.max_blobs, 22)
     finally:
-        ctx.set_sat_free(True)
         ctx.set_fused_gradcirc(True)
     for i, wt in enumerate(wants):
         common.assert_float_images_equal(circ[i], wt["circ"])

@@ -30,12 +30,12 @@ def full_size_case(sensor_w, sensor_h, k2=0.0, tilt=0.0, fmt=0, n_frames=1, n_ro
     return common.to_vpo(lp), frames
 
 
-@pytest.mark.parametrize("flow", ["gradcirc", "rowsums", "sat"])
+@pytest.mark.parametrize("flow", ["gradcirc", "rowsums"])
 @pytest.mark.parametrize("radius", list(range(1, 14)))
 def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
     """circle_radius 1..12 are template instantiations of the fused gradient + circularity kernel (flow 'gradcirc', the
-    default), of the streaming circularity kernel over row sums ('rowsums') and over a materialised SAT ('sat'); 13 takes
-    the unfused generic path; a lone frame (host API, latency path) and a batch of five distinct frames (device API) each
+    default) and of the streaming circularity kernel over row sums ('rowsums'); 13 takes the materialised-SAT path with the
+    unfused circle kernel; a lone frame (host API, latency path) and a batch of five distinct frames (device API) each
     against the oracle."""
     frames = []
     for s_ in range(5):
@@ -47,13 +47,11 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
     wants = [port.detect(f, p) for f in frames]
     assert any(len(w["matches"]) > 0 for w in wants)
     vp = common.to_vp(p)
-    ctx.set_sat_free(flow != "sat")
     ctx.set_fused_gradcirc(flow == "gradcirc")
     try:
         got1 = ctx.detect(frames[0], vp)
         got = common.detect_device(ctx, frames, vp)
     finally:
-        ctx.set_sat_free(True)
         ctx.set_fused_gradcirc(True)
     np.testing.assert_array_equal(got1["flat"], wants[0]["flat"])
     np.testing.assert_array_equal(got1["grad"], wants[0]["grad"])
@@ -63,7 +61,7 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
     for i, w in enumerate(wants):
         common.assert_frame_equal(got, i, w)
     gc_fits = p.grad_offset <= 4 and 2 * p.grad_offset <= radius + 2  # else the fused kernel hands over to the row-sum flow
-    assert got["plan"]["circ"] == (0 if radius == 13 else {"gradcirc": 4 if gc_fits else 3, "rowsums": 3, "sat": 2}[flow])
+    assert got["plan"]["circ"] == (0 if radius == 13 else {"gradcirc": 4 if gc_fits else 3, "rowsums": 3}[flow])
 
 
 @pytest.mark.parametrize("offset", [0, 1, 3])

@@ -23,10 +23,8 @@ ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--group", type=int, default=0)
 ap.add_argument("--lanes", type=int, default=3)
 ap.add_argument("--direct", action="store_true", help="direct-gather reprojection instead of the staged kernel")
-ap.add_argument("--reproject", type=int, default=2, help="0 direct gather, 1 staged per frame, 2 staged + frame-invariant part hoisted (default)")
+ap.add_argument("--reproject", type=int, default=2, help="0 direct gather, 2 staged + frame-invariant part hoisted (default)")
 ap.add_argument("--chunk", type=int, default=0, help="frames per CTA of the hoisted reprojection (0 = automatic)")
-ap.add_argument("--tiled-circ", action="store_true", help="shared-memory tiled circularity kernel instead of the streaming one")
-ap.add_argument("--fused-sat", action="store_true", help="single-pass gradient+SAT kernel instead of row scan + column scan")
 ap.add_argument("--width", type=int, default=2448)
 ap.add_argument("--height", type=int, default=2048)
 ap.add_argument("--no-gradcirc", action="store_true", help="row sums + streaming circularity instead of the fused gradient + circularity kernel")
@@ -53,8 +51,6 @@ ctx.set_group(args.group)
 ctx.set_lanes(args.lanes)
 ctx.set_staged_reproject(0 if args.direct else args.reproject)
 ctx.set_hoist_chunk(args.chunk)
-ctx.set_stream_circ(not args.tiled_circ)
-ctx.set_fused_sat(args.fused_sat)
 ctx.set_fused_gradcirc(not args.no_gradcirc)
 
 

@@ -14,14 +14,15 @@
  *   grad  : four DP4A per pixel, stored once (8-byte stores);
  *   V     : per column the sum of the last K gradient rows (register ring, packed fp32x2 adds);
  *   Q     : horizontal K-window of V by warp shuffles: QA = columns (x+1, x+R], QB = columns (x-R, x-1];
- *   circ  : pp = QA(y+1)  nn = QB(y-R)  pn = -QA(y-R)  np = -QB(y+1), min, exact division by R*R (3 operations, see k_circ_peaks),
+ *   circ  : pp = QA(y+1)  nn = QB(y-R)  pn = -QA(y-R)  np = -QB(y+1), min, exact division by R*R (3 operations: q0 = m*y, e = fma(-q0,d,m), q = fma(e,y,q0) with y = RN(1/d) is the correctly rounded quotient for
+ *           all |m| <= 2^24, d = R*R, R <= 24; tests/test_exact_division.py checks every case),
  *           stored once; the last rows stay in registers for the 4-neighbour peak test (one vote per group, almost never taken).
  *
  * Per pixel ~38 instructions, 4 B read + 8 B written.  Every sum is an exact integer in fp32 as long as the reference's own
  * summed-area table stays below 2^22 in magnitude (SAT_EXACT_LIMIT); then any summation order gives the reference's bits.
  * The kernel also emits, per row segment and column, the column sum of gradDot and the largest magnitude it reached on the
  * way; sat_bound_exceeded_g() turns those into a conservative bound of |SAT| over the whole frame.  Frames that leave
- * the bound are redone in the reference's sequential order (k_sat_fix_clear + k_circ_stream's literal path).
+ * the bound are redone in the reference's sequential order (k_fallback_frame).
  *
  * Clamped taps (CLAMP_TO_EDGE): with clamped SAT taps a box of satBlobCenter.cl:37-40 is still a window sum in which column 0
  * and row 0 never take part and columns >= w / rows >= h do not exist -- the windows below simply treat those as zero.

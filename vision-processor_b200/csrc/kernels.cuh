@@ -283,14 +283,14 @@ __global__ void __launch_bounds__(256) k_reproject(Src src, size_t src_frame_str
 }
 
 /* ------------------------------------------------------------------------------------------------
- * K1, shared-memory staged form (Bayer, bilinear-RTE): the hot kernel of the fused path.
+ * K1, shared-memory staged forms (Bayer, bilinear-RTE): the hot kernels of the fused path.
  *
  * The direct kernel above spends most of its issue slots on address arithmetic, clamps and u8->fp32 conversions of
- * 16 gathered texels per pixel.  Here a CTA owns a 64x16 tile of the flat image; the quads its pixels can touch (known
- * per camera geometry: k_tile_table) are staged ONCE into shared memory as four fp32 planes -- 16-byte coalesced loads
- * of raw Bayer rows, de-interleaved and converted on the way in, edge texels replicated so that CLAMP_TO_EDGE needs no
- * per-tap clamp -- and every tap becomes one LDS with an immediate offset.  Tiles whose footprint does not fit (extreme
- * perspective) or whose coordinates are not finite fall back to the direct path pixel by pixel; results are identical.
+ * 16 gathered texels per pixel.  The staged kernels give a CTA a 64x16 tile of the flat image; the quads its pixels can touch
+ * (known per camera geometry: k_tile_table) are staged into shared memory -- 16-byte coalesced copies of raw Bayer rows,
+ * de-interleaved on the way in, edge texels replicated so that CLAMP_TO_EDGE needs no per-tap clamp -- and every tap
+ * becomes one LDS with an immediate offset.  Tiles whose footprint does not fit (extreme perspective) or whose coordinates are
+ * not finite fall back to the direct path pixel by pixel; results are identical.
  * ---------------------------------------------------------------------------------------------- */
 constexpr int FT_W = 64, FT_H = 16;   /* flat tile */
 constexpr int TQ_W = 80, TQ_H = 24;   /* staged quads per plane (capacity) */
@@ -381,125 +381,6 @@ __device__ __forceinline__ void axis_staged2(float2 u, int origin_magic, int& i0
 	oma = sub2(make_float2(1.0f, 1.0f), a);
 }
 
-/* two bilinear samples at once from staged planes: sample k taps tk[0], tk[1], tk[TQ_W], tk[TQ_W+1] */
-__device__ __forceinline__ void blend_rte_staged2(const float* __restrict__ t0, const float* __restrict__ t1, float2 xa, float2 xoma, float2 ya, float2 yoma,
-                                                  uint32_t& v0, uint32_t& v1)
-{
-	const float2 w00 = mul2(xoma, yoma), w10 = mul2(xa, yoma), w01 = mul2(xoma, ya), w11 = mul2(xa, ya);
-	const float2 p00 = mul2(w00, make_float2(t0[0], t1[0]));
-	const float2 p10 = mul2(w10, make_float2(t0[1], t1[1]));
-	const float2 p01 = mul2(w01, make_float2(t0[TQ_W], t1[TQ_W]));
-	const float2 p11 = mul2(w11, make_float2(t0[TQ_W + 1], t1[TQ_W + 1]));
-	float2 val; /* scalar accumulation, see the note at add2/mul2 */
-	val.x = __fadd_rn(__fadd_rn(__fadd_rn(p00.x, p10.x), p01.x), p11.x);
-	val.y = __fadd_rn(__fadd_rn(__fadd_rn(p00.y, p10.y), p01.y), p11.y);
-	const float2 rn = add2(val, make_float2(8388608.0f, 8388608.0f)); /* RNE to integer in the mantissa */
-	v0 = min(__float_as_uint(rn.x) - 0x4B000000u, 255u);
-	v1 = min(__float_as_uint(rn.y) - 0x4B000000u, 255u);
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
-                                                           const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq, int wf,
-                                                           int hf)
-{
-	__shared__ __align__(16) float T[4 * TQ_H * TQ_W];
-	const int tx = blockIdx.x, ty = blockIdx.y;
-	const uint8_t* raw = raw0 + (size_t)blockIdx.z * frame_stride;
-	uint32_t* out = flat + (size_t)blockIdx.z * wf * hf;
-	const TileEntry e = table[ty * gridDim.x + tx];
-	const int tid = threadIdx.x;
-	const int lx = tid & 63, ly = tid >> 6;
-	const int gx = tx * FT_W + lx;
-
-	if (!(e.flags & 1)) { /* footprint does not fit: direct gather */
-#pragma unroll 1
-		for (int k = 0; k < 4; k++) {
-			const int gy = ty * FT_H + ly + 4 * k;
-			if (gx < wf && gy < hf) {
-				const float2 pos = __ldg(lut + (gy * wf + gx));
-				uint32_t v;
-				if (fabsf(pos.x) < 1048576.0f && fabsf(pos.y) < 1048576.0f) {
-					v = reproject_bayer_rte_fast<FMT>(raw, wq, hq, pos.x, pos.y);
-				} else {
-					uint32_t r, g, b;
-					const SrcBayer s{ raw, 2 * wq };
-					demosaic<FMT, MODE_RTE>(s, wq, hq, pos.x, pos.y, r, g, b);
-					v = drgb(r, g, b);
-				}
-				out[gy * wf + gx] = v;
-			}
-		}
-		return;
-	}
-
-	const int row_bytes = 2 * wq;
-	if (e.flags & 2) {
-		/* 16-byte vectors: raw row 2*qy + s holds planes (2s, 2s+1) of quad row qy interleaved, 8 quads per vector.
-		 * CLAMP_TO_EDGE is resolved here: rows outside the image repeat the edge row; a vector entirely left (right) of the
-		 * image repeats the first (last) quad of the row -- ib and wq are multiples of 8, so no vector straddles the edge. */
-		constexpr int NV = TQ_W / 8;
-		const int total = NV * 2 * e.height;
-		for (int v = tid; v < total; v += 256) {
-			const int rr = v / NV, cv = v - rr * NV;
-			const int qy = clampi(e.jb + (rr >> 1), 0, hq - 1);
-			const int qx0 = e.ib + cv * 8;
-			const int qxc = clampi(qx0, 0, wq - 8);
-			uint4 q = __ldg(reinterpret_cast<const uint4*>(raw + ((2 * qy + (rr & 1)) * row_bytes + 2 * qxc)));
-			if (qx0 != qxc) { /* replicate the edge quad's two bytes over the whole vector */
-				const uint32_t edge = qx0 < 0 ? (q.x & 0xFFFFu) : (q.w >> 16);
-				q.x = q.y = q.z = q.w = edge * 0x00010001u;
-			}
-			float* d0 = T + ((rr & 1) * 2 * TQ_H + (rr >> 1)) * TQ_W + cv * 8; /* plane 2s */
-			float* d1 = d0 + TQ_H * TQ_W;                                     /* plane 2s+1 */
-			const uint32_t wds[4] = { q.x, q.y, q.z, q.w };
-			float2 e0[4], e1[4];
-#pragma unroll
-			for (int k = 0; k < 4; k++) { /* bytes 0,2 -> plane 2s; bytes 1,3 -> plane 2s+1; 0x4B0000bb is the float 2^23 + b */
-				const float2 a = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7442)));
-				const float2 b = make_float2(__uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7441)), __uint_as_float(__byte_perm(wds[k], 0x4B000000u, 0x7443)));
-				e0[k] = add2(a, make_float2(-8388608.0f, -8388608.0f));
-				e1[k] = add2(b, make_float2(-8388608.0f, -8388608.0f));
-			}
-			reinterpret_cast<float4*>(d0)[0] = make_float4(e0[0].x, e0[0].y, e0[1].x, e0[1].y);
-			reinterpret_cast<float4*>(d0)[1] = make_float4(e0[2].x, e0[2].y, e0[3].x, e0[3].y);
-			reinterpret_cast<float4*>(d1)[0] = make_float4(e1[0].x, e1[0].y, e1[1].x, e1[1].y);
-			reinterpret_cast<float4*>(d1)[1] = make_float4(e1[2].x, e1[2].y, e1[3].x, e1[3].y);
-		}
-	} else {
-		/* rows not 16-byte aligned (wq % 8 != 0): per-texel gather with the edge replicated */
-		const int total = 4 * e.height * TQ_W;
-		for (int v = tid; v < total; v += 256) {
-			const int rc = v / TQ_W, ii = v - rc * TQ_W; /* rc = 4*jj + c */
-			const int jj = rc >> 2, c = rc & 3;
-			const int qx = clampi(e.ib + ii, 0, wq - 1), qy = clampi(e.jb + jj, 0, hq - 1);
-			const uint32_t b = __ldg(raw + ((2 * qy + (c >> 1)) * row_bytes + 2 * qx + (c & 1)));
-			T[(c * TQ_H + jj) * TQ_W + ii] = u8_to_float(b);
-		}
-	}
-	__syncthreads();
-
-	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
-#pragma unroll
-	for (int k = 0; k < 4; k++) {
-		const int gy = ty * FT_H + ly + 4 * k;
-		if (gx < wf && gy < hf) {
-			const float2 pos = __ldg(lut + (gy * wf + gx));
-			int ixp, ixn, iyp, iyn;
-			float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
-			axis_staged2(add2(make_float2(pos.x, pos.x), make_float2(0.25f, -0.25f)), xmagic, ixp, ixn, ax, ox);
-			axis_staged2(add2(make_float2(pos.y, pos.y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
-			const float* rowp = T + iyp * TQ_W;
-			const float* rown = T + iyn * TQ_W;
-			/* plane 0 at (+,+), 1 at (-,+), 2 at (+,-), 3 at (-,-)  (resampling.cl:65-80) */
-			uint32_t v0, v1, v2, v3;
-			blend_rte_staged2(rowp + ixp, rowp + TQ_H * TQ_W + ixn, ax, ox, make_float2(ay.x, ay.x), make_float2(oy.x, oy.x), v0, v1);
-			blend_rte_staged2(rown + 2 * TQ_H * TQ_W + ixp, rown + 3 * TQ_H * TQ_W + ixn, ax, ox, make_float2(ay.y, ay.y), make_float2(oy.y, oy.y), v2, v3);
-			out[gy * wf + gx] = FMT == FMT_RGGB ? drgb(v0, v1 / 2 + v2 / 2, v3) : drgb(v1, v0 / 2 + v3 / 2, v2);
-		}
-	}
-}
-
 /* ------------------------------------------------------------------------------------------------
  * K1, frame-invariant form: the default of the batched path.
  *
@@ -509,7 +390,7 @@ __global__ void __launch_bounds__(256) k_reproject_staged(const uint8_t* __restr
  * weights (as packed fp32x2 pairs) and staged-plane offsets of its four pixels once, keeps them in registers, and so
  * does the staging plan (which 16-byte raw vectors go where).  Per frame what remains is the arithmetic on the data:
  * 16 LDS + 8 FMUL2 + 12 FADD + 2 FADD2 per pixel and the dRGB pack.  The raw vectors of frame f+1 are fetched before
- * frame f is blended.  Same operations in the same order as k_reproject_staged / the oracle: bit-identical.
+ * frame f is blended.  Same operations in the same order as the direct kernel / the oracle: bit-identical.
  *
  * The integer tail works on the biased words 0x4B000000 + v that the 2^23 add leaves behind (val in [0, 255.5) for
  * weights in [0,1]): (x>>1) keeps the bias halved exactly (it is even), and 2r-g-b cancels it (resampling.cl:86-91).
@@ -1377,81 +1258,6 @@ __global__ void __launch_bounds__(ROWWIDE_MAX_WARPS * 32) k_grad_rowscan_wide(co
 		flag[blockIdx.y] = 1;
 }
 
-/* K2, single pass: gradient + summed-area table of a strip of `srows` rows x full width per CTA (one warp per row).
- *   1. row prefix sums into shared memory (never written to HBM), gradDot to global;
- *   2. column scan inside the strip; the strip's last row (its column aggregates) is published to global memory;
- *   3. the carry of strip b is the sum of the aggregates of strips 0..b-1 of the same frame -- they are published
- *      without waiting on anybody, so there is no serial chain, only a wait for "all earlier strips have published";
- *   4. SAT = local + carry, converted to fp32 (exact inside the bound) and written once.
- * Traffic per frame: flat in (4Nf) + gradDot out (4Nf) + SAT out (4Nf) instead of 20Nf for row scan + column scan.
- * Strip indices are handed out by an atomic ticket per frame, so a CTA only ever waits for CTAs that started before it
- * (forward progress does not depend on the block scheduling order). */
-__global__ void __launch_bounds__(1024) k_grad_sat(const uint32_t* __restrict__ flat, float* __restrict__ grad, float* __restrict__ sat, int wf, int hf,
-                                                   int o, int srows, int n_strips, int* __restrict__ flag, int* __restrict__ ticket,
-                                                   int* __restrict__ ready, int32_t* __restrict__ agg)
-{
-	extern __shared__ int32_t tile[]; /* srows x wf row prefix sums, then strip-local SAT */
-	__shared__ int s_strip;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int f = blockIdx.y;
-	if (tid == 0)
-		s_strip = atomicAdd(ticket + f, 1);
-	__syncthreads();
-	const int b = s_strip;
-	const int y0 = b * srows;
-	const size_t fbase = (size_t)f * wf * hf;
-	bool bad = false;
-	if (warp < srows) {
-		const int y = y0 + warp;
-		int32_t* trow = tile + warp * wf;
-		if (y < hf) {
-			bad = row_gradscan(flat + fbase, y, wf, hf, o, lane, grad + fbase + y * wf, trow);
-		} else {
-			for (int x = lane; x < wf; x += 32)
-				trow[x] = 0;
-		}
-	}
-	__syncthreads();
-	const int nthreads = blockDim.x;
-	int32_t* my_agg = agg + ((size_t)f * n_strips + b) * wf;
-	for (int x = tid; x < wf; x += nthreads) {
-		int s = 0;
-		for (int r = 0; r < srows; r++) {
-			s += tile[r * wf + x];
-			tile[r * wf + x] = s;
-		}
-		__stcg(my_agg + x, s);
-	}
-	__threadfence();
-	__syncthreads();
-	volatile int* rdy = ready + (size_t)f * n_strips;
-	if (tid == 0)
-		atomicExch(ready + (size_t)f * n_strips + b, 1);
-	if (tid < b) {
-		while (rdy[tid] == 0)
-			__nanosleep(64);
-	}
-	__threadfence();
-	__syncthreads();
-	const int32_t* fagg = agg + (size_t)f * n_strips * wf;
-	float* fsat = sat + fbase;
-	for (int x = tid; x < wf; x += nthreads) {
-		int c = 0;
-		for (int k = 0; k < b; k++)
-			c += __ldcg(fagg + k * wf + x);
-		for (int r = 0; r < srows; r++) {
-			const int y = y0 + r;
-			if (y < hf) {
-				const int v = tile[r * wf + x] + c;
-				bad |= abs(v) >= SAT_EXACT_LIMIT;
-				fsat[y * wf + x] = (float)v;
-			}
-		}
-	}
-	if (bad)
-		flag[f] = 1;
-}
-
 /* K2b: column prefix sums of the row sums -> SAT (satVertical.cl:22-31), exact in int32 (a
  * wrapped value can only appear after an exactly detected excursion beyond 2^24).  One CTA = 32 columns x all
  * rows; warp w owns rows [w*rpw, (w+1)*rpw) held in registers, warp totals are exchanged through shared memory. */
@@ -1613,7 +1419,7 @@ __device__ __forceinline__ int peak_class(const uint32_t* __restrict__ img, cons
 }
 
 /* Compaction scratch (per frame): rowcount[hf] = blobs per row, masks[hf][ceil(wf/32)] = one bit per blob pixel.
- * Pass A (k_circ_peaks on the fused path, k_peaks_count for the stage API) classifies every pixel once, writes the
+ * Pass A (k_grad_circ / k_circ_stream_rs on the fused path, k_peaks_count for the stage API and the generic radius) classifies every pixel once, writes the
  * bit masks, counts blobs per row and accumulates counter[0..2]; pass B (k_peaks_emit) ranks the set bits in raster
  * order (first slot + blobs of earlier rows + blobs to the left) and writes the records with rank < max_matches. */
 
@@ -1654,384 +1460,10 @@ __global__ void __launch_bounds__(256) k_peaks_count(const uint32_t* __restrict_
 	publish_counters(threadIdx.x & 31, counter + 3 * f, nb, ns, np);
 }
 
-/* K3 (fused path): circularity (satBlobCenter.cl:22-42) + peak classification (blobList.cl:38-81) of a 64x32 tile,
- * specialised on the radius R so that every tile dimension and tap offset is an immediate.
- * Away from the image border and inside the exactness bound each quadrant score is a box sum
- *   Q(u,v) = S(u+k,v+k) - S(u+k,v) - S(u,v+k) + S(u,v),  k = R-1:
- *   pp(x,y) = Q(x+1,y+1), nn = Q(x-R,y-R), pn = -Q(x+1,y-R), np = -Q(x-R,y+1)
- * so one shared Q map (4 SAT taps per entry, each SAT value loaded ~2.7 times per entry from L1/L2 by walking down a
- * column with a register window) replaces 16 taps per pixel.  Every intermediate is an exact integer below 2^24, so the
- * bits equal the reference's left-to-right evaluation, and the division by R*R is done with the exact 3-operation
- * sequence q0 = m*y, e = fma(-q0,d,m), q = fma(e,y,q0) (y = RN(1/d)), which is the correctly rounded quotient for all
- * |m| <= 2^24, d = R*R, R <= 24 (tests/test_exact_division.py checks every case).  Border pixels and flagged frames use
- * the literal 16-tap form with IEEE division.  Circularities of the tile plus a 1-pixel ring stay in shared memory for
- * the 4-neighbour peak test. */
-constexpr int CT_W = 64, CT_H = 32;
-constexpr int CIRC_PEAKS_MAX_R = 12;
-
-
-__device__ __noinline__ float circle_px_generic(const float* __restrict__ sat, int w, int h, int x, int y, int r)
-{
-	return circle_px(sat, w, h, x, y, r, (float)(r * r));
-}
-
-template <int R>
-__global__ void __launch_bounds__(256) k_circ_peaks(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
-                                                    int w, int h, float thr, float min_score, int radius, int need_score,
-                                                    const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                                                    uint32_t* __restrict__ masks, int wpr)
-{
-	constexpr int K = R - 1;
-	constexpr int QW = CT_W + R + 3, QH = CT_H + R + 3; /* Q map: u in [x0-1-R, x0+CT_W+1] */
-	constexpr int CW = CT_W + 2, CH = CT_H + 2;         /* circularity: x in [x0-1, x0+CT_W] */
-	constexpr int NRG = 256 / QW;                       /* row groups walking down the Q columns */
-	constexpr int RPG = (QH + NRG - 1) / NRG;
-	__shared__ float Q[QH * QW];
-	__shared__ float Cc[CH * CW];
-	const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H, f = blockIdx.z;
-	const size_t fbase = (size_t)f * w * h;
-	const float* satf = sat + fbase;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const bool flagged = flag[f] != 0;
-	const int qx0 = x0 - 1 - R, qy0 = y0 - 1 - R;
-	/* every SAT tap of every Q entry and every pixel of the ring lies inside the image: no clamping in this CTA */
-	const bool inner = qx0 >= 0 && x0 + CT_W + R <= w - 1 && qy0 >= 0 && y0 + CT_H + R <= h - 1;
-
-	if (!flagged) {
-		const int g = tid / QW, i = tid - g * QW;
-		if (g < NRG) {
-			const int j0 = g * RPG;
-			float a[RPG + K], b[RPG + K];
-			if (inner) {
-				const float* p = satf + ((qy0 + j0) * w + (qx0 + i));
-#pragma unroll
-				for (int j = 0; j < RPG + K; j++) {
-					const bool ok = j0 + j < QH + K;
-					a[j] = ok ? __ldg(p + j * w) : 0.f;
-					b[j] = ok ? __ldg(p + j * w + K) : 0.f;
-				}
-			} else {
-				const int xa = clampi(qx0 + i, 0, w - 1), xb = clampi(qx0 + i + K, 0, w - 1);
-#pragma unroll
-				for (int j = 0; j < RPG + K; j++) {
-					const float* row = satf + clampi(qy0 + j0 + j, 0, h - 1) * w;
-					a[j] = __ldg(row + xa);
-					b[j] = __ldg(row + xb);
-				}
-			}
-#pragma unroll
-			for (int j = 0; j < RPG; j++)
-				if (j0 + j < QH)
-					Q[(j0 + j) * QW + i] = __fadd_rn(__fsub_rn(__fsub_rn(b[j + K], b[j]), a[j + K]), a[j]);
-		}
-	}
-	__syncthreads();
-
-	constexpr float D = (float)(R * R);
-	constexpr float Y = 1.0f / D; /* correctly rounded reciprocal */
-	float* circf = circ_out + fbase;
-	/* walk the (CT_W+2) x (CT_H+2) ring tile with stride 256 without dividing: 256 = (256/CW)*CW + 256%CW */
-	int cj = tid / CW, ci = tid - cj * CW;
-#pragma unroll 3
-	for (int it = 0; it < (CW * CH + 255) / 256; it++) {
-		if (cj < CH) {
-			const int px = x0 - 1 + ci, py = y0 - 1 + cj;
-			float c;
-			if (inner && !flagged) {
-				/* Q index of image coordinate u is u - (x0-1-R): Q(px-R, .) sits at ci, Q(px+1, .) R+1 further */
-				const float* q = Q + (cj * QW + ci);
-				const float pp = q[(R + 1) * QW + (R + 1)];
-				const float nn = q[0];
-				const float pn = __fsub_rn(0.0f, q[R + 1]);        /* 0 - Q keeps +0 where the reference's last addition yields +0 */
-				const float np = __fsub_rn(0.0f, q[(R + 1) * QW]);
-				const float m = fminf(fminf(pp, nn), fminf(pn, np));
-				const float q0 = __fmul_rn(m, Y);
-				c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0); /* == m / D, satBlobCenter.cl:41 */
-			} else {
-				const int cx = clampi(px, 0, w - 1), cy = clampi(py, 0, h - 1);
-				if (!flagged && cx - R >= 0 && cx + R <= w - 1 && cy - R >= 0 && cy + R <= h - 1) {
-					const float* q = Q + ((cy - (y0 - 1)) * QW + (cx - (x0 - 1)));
-					const float m = fminf(fminf(q[(R + 1) * QW + (R + 1)], q[0]), fminf(__fsub_rn(0.0f, q[R + 1]), __fsub_rn(0.0f, q[(R + 1) * QW])));
-					const float q0 = __fmul_rn(m, Y);
-					c = __fmaf_rn(__fmaf_rn(-q0, D, m), Y, q0);
-				} else {
-					c = circle_px_generic(satf, w, h, cx, cy, R);
-				}
-			}
-			Cc[cj * CW + ci] = c;
-			if ((unsigned)(ci - 1) < (unsigned)CT_W && (unsigned)(cj - 1) < (unsigned)CT_H && px < w && py < h)
-				circf[py * w + px] = c;
-		}
-		ci += 256 % CW;
-		cj += 256 / CW;
-		if (ci >= CW) {
-			ci -= CW;
-			cj++;
-		}
-	}
-	__syncthreads();
-
-	/* peak classification: warp -> 4 rows x 2 segments of 32 pixels; almost every segment is entirely below the threshold */
-	int nb = 0, ns = 0, npk = 0;
-	int32_t* rc = rowcount + f * h;
-	uint32_t* mk = masks + (size_t)f * h * wpr;
-#pragma unroll 1
-	for (int q = 0; q < 8; q++) {
-		const int ty = warp * 4 + (q >> 1), tx = (q & 1) * 32 + lane;
-		const int x = x0 + tx, y = y0 + ty;
-		const float* cc = Cc + (ty + 1) * CW + tx + 1;
-		const float c = cc[0];
-		const bool cand = x < w && y < h && !(c < thr); /* blobList.cl:39 */
-		if (!__any_sync(0xffffffffu, cand))
-			continue;
-		int cls = 0;
-		if (cand) {
-			if (cc[-1] > c || cc[1] > c || cc[-CW] > c || cc[CW] > c) /* :47-55; the ring holds the clamped neighbours */
-				cls = 1;
-			else
-				cls = need_score ? classify_by_score(flat + fbase, w, h, x, y, radius, c, min_score) : 3; /* :79 */
-		}
-		publish_segment(cls, lane, rc, mk, wpr, y, (x0 >> 5) + (q & 1), nb, ns, npk);
-	}
-	publish_counters(lane, counter + 3 * f, nb, ns, npk);
-}
-
-/* K3, register-streaming form: the fused circularity + peak kernel with no shared memory and no barriers.
- *
- * A warp walks DOWN a strip of the image, lane = column.  Per row it loads two SAT values per lane (columns u = x+1 and
- * u+k), forms the box sum Q(u, v) = S(u+k,v+k) - S(u+k,v) - S(u,v+k) + S(u,v) against the values it loaded k rows
- * earlier (register ring), fetches Q(x-R, v) from the lane R+1 to its left (one shuffle), and combines the Q rows v and
- * v-R-1 (ring) into the circularity of row y = v-1:
- *     pp = Q(x+1,y+1)  nn = Q(x-R,y-R)  pn = -Q(x+1,y-R)  np = -Q(x-R,y+1)      (satBlobCenter.cl:37-41)
- * The last three circularity rows stay in registers for the 4-neighbour peak test of row y-1 (left/right neighbours by
- * shuffle).  All rings have depth R+2 and the row loop is unrolled by R+2, so every ring index is a compile-time
- * constant.  ~25 instructions per lane and row; lanes 0..R+1 and 31 only feed their neighbours (strip = 29-R columns).
- * Exactness: as for the tiled form above (box sums of exact integers, exact 3-operation division); pixels within R of
- * the image border and flagged frames take the literal 16-tap form with IEEE division. */
-/* circularity of the pixels within r of the image border (CLAMP_TO_EDGE acts on their taps): literal 16-tap form, one
- * thread per pixel of the border frame (2.1 % of a 1224x1024 image).  Runs before k_circ_stream, which reads these values
- * back instead of computing them in divergent lanes. */
-__global__ void __launch_bounds__(256) k_circ_border(const float* __restrict__ sat, float* __restrict__ circ_out, int w, int h, int r,
-                                                     const int* __restrict__ flag)
-{
-	const int f = blockIdx.y;
-	if (flag[f] != 0)
-		return; /* flagged frames are computed entirely by the generic path of k_circ_stream */
-	const int id = blockIdx.x * 256 + threadIdx.x;
-	const int rr = min(r, h / 2), rc = min(r, w / 2); /* border thickness if the image is smaller than 2r */
-	const int top = rr * w, mid_h = h - 2 * rr;
-	int x, y;
-	if (id < top) {
-		y = id / w;
-		x = id - y * w;
-	} else if (id < 2 * top) {
-		const int k = id - top;
-		y = k / w;
-		x = k - y * w;
-		y += h - rr;
-	} else {
-		const int k = id - 2 * top;
-		if (k >= mid_h * 2 * rc)
-			return;
-		y = k / (2 * rc);
-		const int c = k - y * 2 * rc;
-		y += rr;
-		x = c < rc ? c : w - 2 * rc + c;
-	}
-	const size_t fbase = (size_t)f * w * h;
-	circ_out[fbase + y * w + x] = circle_px(sat + fbase, w, h, x, y, r, (float)(r * r));
-}
-
-
-template <int R>
-__global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream(const float* __restrict__ sat, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
-                                                     int w, int h, int seg_rows, float thr, float min_score, int radius, int need_score,
-                                                     const int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                                                     uint32_t* __restrict__ masks, int wpr, int only_flagged)
-{
-	if (only_flagged && flag[blockIdx.z] == 0)
-		return; /* second pass of the SAT-free flow: only frames that left the exactness bound are redone here */
-	constexpr int K = R - 1, D = R + 2;
-	constexpr int LO = R + 2;          /* first output lane: needs Q from lane-(R+1) and a circularity from lane-1 */
-	constexpr int SWU = 32 - LO - 1;   /* output lanes LO..30 */
-	constexpr float DIV = (float)(R * R);
-	constexpr float RCP = 1.0f / DIV;
-	const int lane = threadIdx.x & 31;
-	const int strip = blockIdx.x * 4 + (threadIdx.x >> 5);
-	const int f = blockIdx.z;
-	const int xs = strip * SWU;
-	if (xs >= w)
-		return;
-	const int x = xs + lane - LO;                       /* this lane's pixel column (may be outside the image) */
-	const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);
-	const size_t fbase = (size_t)f * w * h;
-	const float* satf = sat + fbase;
-	float* circf = circ_out + fbase;
-	const uint32_t* flatf = flat + fbase;
-	const bool x_in = x >= 0 && x < w;
-	const bool out_lane = lane >= LO && lane <= 30 && x < w; /* x >= 0 follows from lane >= LO */
-	const bool used_lane = x_in && lane >= LO - 1;            /* output lanes and their left/right neighbours inside the image */
-	int nb = 0, ns = 0, npk = 0;
-	int32_t* rcf = rowcount + f * h;
-	uint32_t* mkf = masks + (size_t)f * h * wpr;
-
-	auto publish = [&](int cls, int yy) { /* warp-uniform call */
-		if (cls == 3) {
-			atomicOr(mkf + (yy * wpr + (x >> 5)), 1u << (x & 31));
-			atomicAdd(rcf + yy, 1);
-		}
-		nb += __popc(__ballot_sync(0xffffffffu, cls == 3));
-		ns += __popc(__ballot_sync(0xffffffffu, cls == 2));
-		npk += __popc(__ballot_sync(0xffffffffu, cls == 1));
-	};
-
-	if (flag[f] != 0) {
-		/* Flagged frame (a sum left the exactness bound): literal 16-tap form for every pixel, three rows in registers. */
-		float c2 = 0.f, c1 = 0.f;
-		for (int y = ys - 1; y <= ye; y++) {
-			float c = 0.f;
-			if (used_lane && y >= 0 && y < h)
-				c = circle_px_generic(satf, w, h, x, y, R);
-			if (out_lane && y >= ys && y < ye)
-				circf[y * w + x] = c;
-			const int yy = y - 1;
-			const bool cand = out_lane && yy >= ys && yy < ye && !(c1 < thr);
-			if (__any_sync(0xffffffffu, cand)) {
-				const float cl = __shfl_up_sync(0xffffffffu, c1, 1), crr = __shfl_down_sync(0xffffffffu, c1, 1);
-				const int cls = cand ? classify_px(flatf, w, h, x, yy, radius, thr, min_score, need_score, c1, x > 0 ? cl : c1, x < w - 1 ? crr : c1,
-				                                   yy > 0 ? c2 : c1, yy < h - 1 ? c : c1)
-				                     : 0;
-				publish(cls, yy);
-			}
-			c2 = c1;
-			c1 = c;
-		}
-		publish_counters(lane, counter + 3 * f, nb, ns, npk);
-		return;
-	}
-
-	/* SAT columns of Q(x+1, .): u = x+1 and u+K.  Lanes whose u or u+K fall outside the image produce a Q that only border
-	 * pixels would use (those read the value k_circ_border computed), so u is merely kept inside the row: the u+K load may
-	 * run up to K floats past the row end, which stays inside the (padded) SAT scratch. */
-	const int ua = clampi(x + 1, 0, w - 1);
-	const bool lane_border = !(x - R >= 0 && x + R <= w - 1);
-	const bool warp_has_border_lane = __any_sync(0xffffffffu, used_lane && lane_border);
-	const float* pa = satf + ua;
-	float* pc = circf + (x_in ? x : 0);
-
-	/* H(t) = S(u+K, t) - S(u, t); Q(u, v) = H(v+K) - H(v).  (The reference evaluates ((S11 - S10) - S01) + S00; inside the
-	 * exactness bound every partial result is an exact integer below 2^24, so the order is irrelevant.) */
-	float la[D], lb[D], cb[D], hn[D], hold[K > 0 ? K : 1], qa[D], qb[D], cr[D], cbc[D];
-#pragma unroll
-	for (int i = 0; i < D; i++)
-		hn[i] = qa[i] = qb[i] = cr[i] = cb[i] = cbc[i] = 0.f;
-	const int t0 = ys - 1 - R;
-	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
-
-	/* loads of one group: D SAT rows (rows outside the image repeat the edge row: CLAMP_TO_EDGE in y) and, where the
-	 * group touches the image border, the circularities k_circ_border prepared for this lane's pixels */
-	auto load_group = [&](int t) {
-		if (t >= 0 && t + D - 1 <= h - 1) { /* warp-uniform: no row of the group is clamped */
-			const float* p = elem_ptr(pa, (unsigned)(t * w));
-#pragma unroll
-			for (int s = 0; s < D; s++) {
-				la[s] = __ldg(p);
-				lb[s] = __ldg(p + K);
-				p += w;
-			}
-		} else {
-#pragma unroll
-			for (int s = 0; s < D; s++) {
-				const float* p = elem_ptr(pa, (unsigned)(clampi(t + s, 0, h - 1) * w));
-				la[s] = __ldg(p);
-				lb[s] = __ldg(p + K);
-			}
-		}
-		const int y0 = t - R; /* circularity rows of the group: y0 .. y0+D-1 */
-		if (warp_has_border_lane || y0 < R || y0 + D - 1 > h - 1 - R) { /* warp-uniform */
-#pragma unroll
-			for (int s = 0; s < D; s++) {
-				const int y = y0 + s;
-				if (used_lane && y >= 0 && y < h && (lane_border || y < R || y > h - 1 - R))
-					cb[s] = __ldcg(elem_ptr(pc, (unsigned)(y * w)));
-			}
-		}
-	};
-
-	load_group(t0);
-	for (int g = 0; g < n_groups; g++) {
-		const int t = t0 + g * D;
-		/* consume this group's loads, then put the next group's loads in flight before the arithmetic of this one */
-#pragma unroll
-		for (int i = 0; i < K; i++)
-			hold[i] = hn[D - K + i];
-#pragma unroll
-		for (int s = 0; s < D; s++) {
-			hn[s] = __fsub_rn(lb[s], la[s]);
-			cbc[s] = cb[s];
-		}
-		if (g + 1 < n_groups)
-			load_group(t + D);
-
-		/* Straight-line code for the D rows of the group: the shuffles and the short dependent chains of different rows
-		 * overlap; ONE vote per group decides whether any pixel reaches the threshold at all (almost never), and only then
-		 * are the rows classified one by one. */
-		constexpr int DD = 4 * D;
-		const int y0 = t - R; /* circularity row of step 0 */
-		float crow[D + 2]; /* circularity rows y0-2 .. y0+D-1 */
-		crow[0] = cr[(0 - R - 2 + DD) % D];
-		crow[1] = cr[(0 - R - 1 + DD) % D];
-#pragma unroll
-		for (int s = 0; s < D; s++) {
-			const int so = (s - K + DD) % D, sq = (s - 2 * R + DD) % D, sc = (s - R + DD) % D;
-			const float h_old = s - K >= 0 ? hn[s - K >= 0 ? s - K : 0] : hold[s - K >= 0 ? 0 : s];
-			const float q = __fsub_rn(hn[s], h_old); /* Q row v = t+s-K */
-			qa[so] = q;
-			qb[so] = __shfl_up_sync(0xffffffffu, q, R + 1);
-			const float m = fminf(fminf(qa[so], qb[sq]), fminf(__fsub_rn(0.0f, qa[sq]), __fsub_rn(0.0f, qb[so])));
-			const float q0 = __fmul_rn(m, RCP);
-			float c = __fmaf_rn(__fmaf_rn(-q0, DIV, m), RCP, q0); /* == m / (R*R), satBlobCenter.cl:41 */
-			const int y = y0 + s;
-			if (lane_border || y < R || y > h - 1 - R)
-				c = cbc[s]; /* border pixel: the value k_circ_border computed (unused lanes/rows carry garbage that is never read) */
-			cr[sc] = c;
-			crow[s + 2] = c;
-			if (out_lane && y >= ys && y < ye)
-				*elem_ptr(pc, (unsigned)(y * w)) = c;
-		}
-		/* rows classified by this group: yy = y0-1 .. y0+D-2, i.e. crow[1 .. D] */
-		float mx = crow[1];
-#pragma unroll
-		for (int s = 2; s <= D; s++)
-			mx = fmaxf(mx, crow[s]);
-		if (__any_sync(0xffffffffu, out_lane && !(mx < thr))) {
-#pragma unroll 1
-			for (int i = 1; i <= D; i++) {
-				const int yy = y0 + i - 2;
-				float cm = crow[1], up = crow[0], dn = crow[2];
-#pragma unroll
-				for (int k = 2; k <= D; k++)
-					if (i == k) {
-						cm = crow[k];
-						up = crow[k - 1];
-						dn = crow[k + 1];
-					}
-				const bool cand = out_lane && yy >= ys && yy < ye && !(cm < thr);
-				if (!__any_sync(0xffffffffu, cand))
-					continue;
-				const float cl = __shfl_up_sync(0xffffffffu, cm, 1), crr = __shfl_down_sync(0xffffffffu, cm, 1);
-				const int cls = cand ? classify_px(flatf, w, h, x, yy, radius, thr, min_score, need_score, cm, x > 0 ? cl : cm, x < w - 1 ? crr : cm,
-				                                   yy > 0 ? up : cm, yy < h - 1 ? dn : cm)
-				                     : 0;
-				publish(cls, yy);
-			}
-		}
-	}
-	publish_counters(lane, counter + 3 * f, nb, ns, npk);
-}
-
 /* ------------------------------------------------------------------------------------------------
- * SAT-free circularity (default of the fused path); no separate border pass.
+ * Streaming circularity from row sums (the row-sum flow: A/B alternative of gradcirc.cuh's fused kernel, and the path of gradient
+ * offsets it does not stage); no summed-area table, no separate border pass.  A warp walks DOWN a strip of the image, lane =
+ * column; rings of depth R+2 and a row loop unrolled by R+2 make every ring index a compile-time constant.
  *
  * satBlobCenter.cl:37-40 only ever uses the summed-area table through four box sums, and a box sum over columns
  * (u, u+K] x rows (v, v+K] is  sum_{y in (v, v+K]} [RS(u+K, y) - RS(u, y)]  with RS the row prefix sums that
@@ -2041,10 +1473,12 @@ __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_s
  * all exact integers in fp32 inside the exactness bound -- bit-identical to the SAT form by the argument at
  * SAT_EXACT_LIMIT.  What the SAT was also needed for is the bound itself (|SAT| < 2^22 everywhere): every lane
  * accumulates the column sum of RS over its segment's rows and the largest magnitude the running sum reached;
- * k_sat_check_fix combines the segments (|SAT(x,y)| <= |carry(x, seg)| + max|local|, conservative) and raises the frame's
+ * k_sat_check_rs combines the segments (|SAT(x,y)| <= |carry(x, seg)| + max|local|, conservative) and raises the frame's
  * flag.  Flagged frames (never seen on camera images) are redone afterwards in the reference's sequential order
- * (k_sat_check_fix, then k_circ_stream's literal path).
+ * (k_sat_check_rs, then k_fallback_frame).
  * ---------------------------------------------------------------------------------------------- */
+
+constexpr int CIRC_STREAM_MAX_R = 12;
 
 template <int R>
 __global__ void __launch_bounds__(128, (R <= 5 ? 6 : (R <= 7 ? 5 : 4))) k_circ_stream_rs(const float* __restrict__ rs, float* __restrict__ circ_out, const uint32_t* __restrict__ flat,
@@ -2330,7 +1764,7 @@ constexpr int EMIT_MAX_ROWS = 128;
 /* pass B: one warp per row that holds at least one blob; blobs are visited in x order, each one by the whole warp.
  * Latency path (segsum != nullptr): the grid has ceil(w/256) more CTAs per frame, which evaluate the exactness bound of
  * the SAT next to the record warps and raise the frame's flag for the HOST to see -- the caller then redoes the frame in
- * sequential order (k_sat_check_fix + k_circ_stream + this kernel again) instead of launching that pair of kernels for
+ * sequential order (k_fallback_frame + this kernel again) instead of launching the check and the fallback for
  * every frame just to have them exit. */
 __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__ img, const float* __restrict__ circ, int w, int h, int radius,
                                                     int max_matches, const int32_t* __restrict__ first_slot, const int32_t* __restrict__ rowcount,
@@ -2434,12 +1868,9 @@ __global__ void __launch_bounds__(256) k_peaks_emit(const uint32_t* __restrict__
 /* per-batch preparation of the compaction scratch: zero the row counts and the exactness flags; either zero the
  * counters (fused path, main.cpp:283-288) or remember counter[0] as the first output slot (stage API). */
 __global__ void k_peaks_prepare(int32_t* __restrict__ counter, int32_t* __restrict__ first_slot, int32_t* __restrict__ rowcount,
-                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag, uint32_t* __restrict__ masks, int n_mask_words,
-                                int* __restrict__ sync_words = nullptr, int n_sync_words = 0)
+                                int n_rows_total, int n_frames, int zero_counters, int* __restrict__ flag, uint32_t* __restrict__ masks, int n_mask_words)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	for (int k = i; k < n_sync_words; k += gridDim.x * blockDim.x)
-		sync_words[k] = 0; /* strip tickets and ready flags of k_grad_sat */
 	for (int k = i; k < n_mask_words; k += gridDim.x * blockDim.x)
 		masks[k] = 0u;
 	if (i < n_rows_total)

@@ -165,27 +165,19 @@ struct vp_ctx {
 	int* flag = nullptr;
 	size_t rows_cap = 0, frames_cap = 0, mask_words_cap = 0;
 	int group = 0; /* 0 = choose from the frame size */
-	int staged_reproject = 2; /* 0 direct gather, 1 staged per frame, 2 staged with frame-invariant weights hoisted */
+	int staged_reproject = 2; /* 0 direct gather, else shared-memory staged with the frame-invariant weights hoisted */
 	int hoist_chunk = 0;      /* frames per CTA of the hoisted kernel; 0 = automatic */
 	int sm_count = 148;
-	bool stream_circ = true;
-	bool fused_gc = true; /* gradient + circularity + classification in one kernel (gradcirc.cuh); needs sat_free */
+	bool fused_gc = true; /* gradient + circularity + classification in one kernel (gradcirc.cuh) vs row sums + streaming circularity */
 	bool gc_attr = false;
-	bool sat_free = true; /* circularity straight from the row sums: no column scan, no materialised SAT (needs stream_circ, !fused_sat) */
 	int32_t* striptot[MAX_LANES] = {}; /* per lane: k_grad_circ's per-row strip sums of gradDot (frames of the group x strips x rows) */
 	size_t striptot_words = 0;
 	float* segsum[MAX_LANES] = {}; /* per lane: column sums of the row sums per (frame of the group, row segment) */
 	float* segmax[MAX_LANES] = {};
 	size_t seg_words = 0;
-	bool fused_sat = false; /* measured slower than row scan + column scan on B200 (profiles/r01_fused_sat_sweep.txt); kept as an A/B option */
-	bool grad_sat_attr = false;
 	bool hoist_attr = false;
 	bool hoist4_attr = false;
 	volatile float one = 1.0f; /* handed to kernels that need a 1.0 the compiler cannot fold (add2_opaque) */
-	int32_t* agg[MAX_LANES_DECL] = {};  /* strip aggregates of k_grad_sat, per lane */
-	size_t agg_words = 0;
-	int* sync_words = nullptr;          /* per frame of a batch: strip ticket + ready flags */
-	size_t sync_cap = 0;
 	int last_fallbacks = 0;
 	int* flag_host = nullptr; /* pinned */
 	int32_t last_plan[8] = {}; /* vp_detect_last_plan */
@@ -440,7 +432,7 @@ int ensure_scratch(vp_ctx* ctx, size_t group_px, size_t rows, size_t frames, siz
 		ctx->scratch_px = 0;
 		for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
 			CK(ctx, cudaMalloc(&ctx->rowsum[l], group_px * 4 + 256)); /* k_circ_stream_rs reads up to R-1 floats past a row end */
-			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4 + 256)); /* k_circ_stream reads up to R-1 floats past a row end */
+			CK(ctx, cudaMalloc(&ctx->sat[l], group_px * 4 + 256)); /* padded like the row sums */
 		}
 		ctx->scratch_px = group_px;
 	}
@@ -546,30 +538,14 @@ __global__ void __launch_bounds__(1024) k_sat_fix(const float* __restrict__ grad
 	sat_fix_frame(grad, hor, sat, w, h, (size_t)blockIdx.x * w * h);
 }
 
-/* SAT-free flow, after the fast pass, one CTA per frame: (1) the exactness bound of the summed-area table from the
- * per-segment column sums, |SAT(x, y)| <= |sum of the segments above| + max |running sum inside the segment|
- * (conservative); (2) for a frame that left the bound -- here or already in the row scan -- forget what the fast pass
- * published and (3) build the SAT in the reference's sequential order for k_circ_stream's literal path. */
-__global__ void __launch_bounds__(1024) k_sat_check_fix(const float* __restrict__ segsum, const float* __restrict__ segmax, int n_seg,
-                                                        const float* __restrict__ grad, float* __restrict__ hor, float* __restrict__ sat, int w, int h,
-                                                        int* __restrict__ flag, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                                                        uint32_t* __restrict__ masks, int wpr)
+/* row-sum flow, after the fast pass, one CTA per frame: the exactness bound of the summed-area table from k_circ_stream_rs's
+ * per-segment column sums of the row sums, |SAT(x, y)| <= |sum of the segments above| + max |running sum inside the segment|
+ * (conservative); raises the flag of a frame that left it (the row scan raised it already if a row sum did) */
+__global__ void __launch_bounds__(1024) k_sat_check_rs(const float* __restrict__ segsum, const float* __restrict__ segmax, int n_seg, int w, int* __restrict__ flag)
 {
 	const int f = blockIdx.x;
-	int state = flag[f];
-	if (state == 0) {
-		if (!sat_bound_exceeded(segsum, segmax, n_seg, w, f, threadIdx.x, 1024))
-			return;
-		if (threadIdx.x == 0)
-			flag[f] = 2;
-	}
-	for (int i = threadIdx.x; i < h * wpr; i += 1024)
-		masks[(size_t)f * h * wpr + i] = 0u;
-	for (int i = threadIdx.x; i < h; i += 1024)
-		rowcount[(size_t)f * h + i] = 0;
-	if (threadIdx.x < 3)
-		counter[3 * f + threadIdx.x] = 0;
-	sat_fix_frame(grad, hor, sat, w, h, (size_t)f * w * h);
+	if (flag[f] == 0 && sat_bound_exceeded(segsum, segmax, n_seg, w, f, threadIdx.x, 1024) && threadIdx.x == 0)
+		flag[f] = 2;
 }
 
 /* Flow of the fused gradient + circularity kernel: the bound has been evaluated (k_sat_check_g / k_peaks_emit).  ONE launch
@@ -620,6 +596,18 @@ __global__ void __launch_bounds__(1024) k_fallback_frame(const uint32_t* __restr
 	publish_counters(lane, counter + 3 * f, nb, ns, np);
 }
 
+/* one-time opt-in to the dynamic shared memory of the one-frame-per-word reprojection kernel (both call sites ask for exactly
+ * HOIST_SMEM) */
+int ensure_hoist_attr(vp_ctx* ctx)
+{
+	if (!ctx->hoist_attr) {
+		CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+		CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
+		ctx->hoist_attr = true;
+	}
+	return VP_OK;
+}
+
 /* rows per CTA of the streaming circularity kernels: 128 (few halo rows per segment) whenever that already gives the GPU two
  * CTAs per SM; fewer frames or smaller images take 64 or 32 rows and trade halo work for shorter dependent chains and a
  * full GPU (a lone 1224x1024 frame has only 14 x 8 CTAs to offer at 128 rows) */
@@ -630,6 +618,12 @@ int circ_seg_rows(const vp_ctx* ctx, int wf, int hf, int n_frames, int r, bool g
 		return seg_env;
 	const int swu = gc ? grad_circ_strip_width(r) : 32 - (r + 2) - 1; /* output columns per warp, see k_grad_circ / k_circ_stream_rs */
 	const long long per_row_of_segments = (long long)cdiv(cdiv(wf, swu > 0 ? swu : 1), 4) * n_frames;
+	/* the fused gradient + circularity kernel recomputes 2(R + offset) rows and runs four predicated groups of rows per segment:
+	 * with a whole batch to spread over the GPU (>= 8 CTAs per SM left) 256-row segments measured 2.5 % faster than 128
+	 * (profiles/r02_sweeps.txt).  (A strip's running sum may wrap int32 at 256 rows on an all-saturated frame; such a frame is
+	 * flagged by the column terms alone, see sat_bound_exceeded_g.) */
+	if (gc && per_row_of_segments * cdiv(hf, 256) >= 8LL * ctx->sm_count)
+		return 256;
 	for (int seg = 128; seg > 32; seg >>= 1)
 		if (per_row_of_segments * cdiv(hf, seg) >= 2LL * ctx->sm_count)
 			return seg;
@@ -788,8 +782,6 @@ void vp_ctx_destroy(vp_ctx* c)
 	if (c->strip_flat[0]) cudaEventDestroy(c->strip_flat[0]);
 	if (c->lone_fork) cudaEventDestroy(c->lone_fork);
 	for (int l = 0; l < vp_ctx::MAX_LANES; l++)
-		cudaFree(c->agg[l]);
-	cudaFree(c->sync_words);
 	cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
 	if (c->flag_host) cudaFreeHost(c->flag_host);
 	c->lone.reset();
@@ -826,18 +818,11 @@ int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group) /* tuning knob used by t
 	return VP_OK;
 }
 
-int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memory staged vs direct-gather reprojection */
+int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memory staged (frame-invariant part hoisted) vs direct-gather reprojection */
 {
 	REQUIRE(ctx, ctx, "ctx is null");
-	REQUIRE(ctx, on >= 0 && on <= 2, "variant must be 0 (direct), 1 (staged) or 2 (staged, frame-invariant part hoisted)");
+	REQUIRE(ctx, on >= 0 && on <= 2, "variant must be 0 (direct gather) or 1/2 (staged, frame-invariant part hoisted)");
 	ctx->staged_reproject = on;
-	return VP_OK;
-}
-
-int vp_ctx_set_sat_free(vp_ctx* ctx, int on) /* A/B switch: circularity from the row sums (no column scan, no SAT) vs from a materialised SAT */
-{
-	REQUIRE(ctx, ctx, "ctx is null");
-	ctx->sat_free = on != 0;
 	return VP_OK;
 }
 
@@ -845,20 +830,6 @@ int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on) /* A/B switch: one gradient +
 {
 	REQUIRE(ctx, ctx, "ctx is null");
 	ctx->fused_gc = on != 0;
-	return VP_OK;
-}
-
-int vp_ctx_set_stream_circ(vp_ctx* ctx, int on) /* A/B switch: register-streaming vs shared-memory tiled circularity+peaks */
-{
-	REQUIRE(ctx, ctx, "ctx is null");
-	ctx->stream_circ = on != 0;
-	return VP_OK;
-}
-
-int vp_ctx_set_fused_sat(vp_ctx* ctx, int on) /* A/B switch: single-pass gradient+SAT kernel vs row scan + column scan */
-{
-	REQUIRE(ctx, ctx, "ctx is null");
-	ctx->fused_sat = on != 0;
 	return VP_OK;
 }
 
@@ -1477,16 +1448,19 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	const int wpr = cdiv(wf, 32);
 	rc = ensure_scratch(ctx, (size_t)G * nf, (size_t)n_frames * hf, n_frames, (size_t)n_frames * hf * wpr);
 	if (rc) return rc;
-	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_PEAKS_MAX_R;
-	const bool sat_free = ctx->sat_free && ctx->stream_circ && !ctx->fused_sat && fused_circ;
-	const bool use_gc = sat_free && ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
+	const bool fused_circ = p->circle_radius >= 1 && p->circle_radius <= CIRC_STREAM_MAX_R;
+	/* three flows after the reprojection: the fused gradient + circularity kernel (default), gradient + row sums followed by the
+	 * streaming circularity kernel (A/B switch; also gradient offsets the fused kernel does not stage), and -- for radii outside
+	 * the specialised range -- a materialised summed-area table with the unfused circle / count kernels */
+	const bool use_gc = fused_circ && ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
+	const bool rowsums = fused_circ && !use_gc;
 	const int seg = circ_seg_rows(ctx, wf, hf, n_frames, p->circle_radius, use_gc);
 	const int n_seg = cdiv(hf, seg);
 	if (use_gc && !ctx->gc_attr) {
 		CK(ctx, (cudaError_t)grad_circ_prepare());
 		ctx->gc_attr = true;
 	}
-	if (sat_free) {
+	if (use_gc || rowsums) {
 		const size_t need = (size_t)G * n_seg * wf;
 		if (need > ctx->seg_words) {
 			CK(ctx, cudaDeviceSynchronize());
@@ -1518,70 +1492,35 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			ctx->striptot_words = need_t;
 		}
 	}
-	/* single-pass gradient + SAT: a strip of srows rows x full width lives in shared memory */
-	int srows = (int)((200u * 1024u) / ((size_t)wf * 4));
-	if (srows > 32) srows = 32;
-	static const int srows_env = getenv("VP_SAT_ROWS") ? atoi(getenv("VP_SAT_ROWS")) : 0; /* tuning aid */
-	if (srows_env > 0 && srows_env < srows) srows = srows_env;
-	const int n_strips = srows > 0 ? cdiv(hf, srows) : 0;
-	const bool fused_sat = ctx->fused_sat && srows >= 8 && n_strips <= 1024;
-	if (fused_sat) {
-		const size_t need_agg = (size_t)G * n_strips * wf, need_sync = (size_t)n_frames * (1 + n_strips);
-		if (need_agg > ctx->agg_words) {
-			CK(ctx, cudaDeviceSynchronize());
-			for (int l = 0; l < vp_ctx::MAX_LANES; l++) {
-				cudaFree(ctx->agg[l]);
-				ctx->agg[l] = nullptr;
-			}
-			ctx->agg_words = 0;
-			for (int l = 0; l < vp_ctx::MAX_LANES; l++)
-				CK(ctx, cudaMalloc(&ctx->agg[l], need_agg * 4));
-			ctx->agg_words = need_agg;
-		}
-		if (need_sync > ctx->sync_cap) {
-			CK(ctx, cudaDeviceSynchronize());
-			cudaFree(ctx->sync_words);
-			ctx->sync_words = nullptr;
-			ctx->sync_cap = 0;
-			CK(ctx, cudaMalloc(&ctx->sync_words, need_sync * 4));
-			ctx->sync_cap = need_sync;
-		}
-		if (!ctx->grad_sat_attr) {
-			CK(ctx, cudaFuncSetAttribute(k_grad_sat, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			ctx->grad_sat_attr = true;
-		}
-	}
 	const float2* lut;
 	const TileEntry* tiles;
 	rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, wf, hf, p->wq, p->hq, &lut, &tiles);
 	if (rc) return rc;
-	const bool staged = ctx->staged_reproject != 0 && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
-	const bool hoisted = staged && ctx->staged_reproject == 2;
+	const bool hoisted = ctx->staged_reproject != 0 && p->fmt != VP_FMT_BGR8 && p->sample_mode == VP_SAMPLE_BILINEAR_RTE;
 	const int ns = need_score(p->circ_threshold, p->min_score);
-	const bool by_strips = plan && plan->n > 1 && n_frames == 1 && hoisted && sat_free && !ctx->profiling;
+	const bool by_strips = plan && plan->n > 1 && n_frames == 1 && hoisted && (use_gc || rowsums) && !ctx->profiling;
 	int* const flags = opts.flags ? opts.flags : ctx->flag;
-	const bool defer_fallback = opts.defer_fallback && sat_free && n_groups == 1; /* only the SAT-free flow has a check to move */
+	const bool defer_fallback = opts.defer_fallback && (use_gc || rowsums) && n_groups == 1; /* only these flows have a check to move */
 	opts.deferred = defer_fallback;
 	int32_t* const plan_out = ctx->last_plan;
-	plan_out[0] = hoisted ? 2 : staged ? 1 : 0;
+	plan_out[0] = hoisted ? 2 : 0;
 	plan_out[1] = 1;
 	plan_out[2] = G;
 	plan_out[3] = lanes;
-	plan_out[4] = use_gc ? 4 : sat_free ? 3 : fused_circ ? (ctx->stream_circ ? 2 : 1) : 0;
+	plan_out[4] = use_gc ? 4 : rowsums ? 3 : 0;
 	plan_out[5] = seg;
 	plan_out[6] = plan_out[7] = 0;
 
 	/* scratch of the compaction (blob masks, row counts, counters, flags) cleared for the whole batch up front -- or, when
 	 * the batch runs as several groups, group by group at the head of each group's lane, so that clearing overlaps the other
 	 * lanes' kernels instead of standing alone before the fork */
-	const bool prepare_per_group = n_groups > 1 && !fused_sat;
+	const bool prepare_per_group = n_groups > 1;
 	if (!prepare_per_group) {
 		Stage st(ctx, "prepare");
 		const int n = n_frames * hf;
 		/* enough CTAs to clear the blob masks of a lone frame in one pass (the kernel strides over them) */
 		const int prep_ctas = std::max(cdiv(n, 256), std::min(cdiv(n * wpr, 256), 4 * ctx->sm_count));
-		k_peaks_prepare<<<prep_ctas, 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, flags, ctx->masks, n * wpr,
-		                                                       fused_sat ? ctx->sync_words : nullptr, fused_sat ? n_frames * (1 + n_strips) : 0);
+		k_peaks_prepare<<<prep_ctas, 256, 0, ctx->stream>>>(d_counter, ctx->first_slot, ctx->rowcount, n, n_frames, 1, flags, ctx->masks, n * wpr);
 		if ((rc = check_launch(ctx, "k_peaks_prepare"))) return rc;
 	}
 	if (lanes > 1) { /* fork: the other lanes start after everything already enqueued on the context stream */
@@ -1604,13 +1543,7 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 		CK(ctx, cudaStreamWaitEvent(sA, ctx->fork, 0));
 		const int tiles_x = cdiv(wf, FT_W), tiles_y = cdiv(hf, FT_H);
 		uint32_t* flat = (uint32_t*)d_flat;
-		if (!ctx->hoist_attr) {
-			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
-			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
-			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
-			CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM));
-			ctx->hoist_attr = true;
-		}
+		if ((rc = ensure_hoist_attr(ctx))) return rc;
 		int ty_done = 0;
 		for (int k = 0; k < plan->n; k++) {
 			CK(ctx, cudaStreamWaitEvent(sA, plan->uploaded[k], 0));
@@ -1663,19 +1596,9 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 				if (ctx->hoist_chunk <= 0) /* an explicit vp_ctx_set_hoist_chunk is taken as it is (tests, sweeps) */
 					while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
-				static const size_t hoist_pad = getenv("VP_HOIST_PAD") ? (size_t)atoi(getenv("VP_HOIST_PAD")) : 0; /* tuning aid: caps residency */
-				const size_t HOIST_SMEM_L = HOIST_SMEM + hoist_pad;
-				static const int hoist_px = getenv("VP_HOIST_PX") ? atoi(getenv("VP_HOIST_PX")) : 4; /* tuning aid: pixels per thread */
-				if (!ctx->hoist_attr) {
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_RGGB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
-					CK(ctx, cudaFuncSetAttribute(k_reproject_hoist<FMT_GRBG, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST_SMEM_L));
-					ctx->hoist_attr = true;
-				}
 				static const int hoist_quads = getenv("VP_HOIST_QUADS") ? atoi(getenv("VP_HOIST_QUADS")) : 1; /* tuning aid / A-B */
 				plan_out[1] = chunk;
-				if (hoist_px == 4 && hoist_quads && chunk >= 4) {
+				if (hoist_quads && chunk >= 4) {
 					plan_out[0] = 4;
 					if (!ctx->hoist4_attr) {
 						CK(ctx, cudaFuncSetAttribute(k_reproject_hoist4<FMT_RGGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HOIST4_SMEM));
@@ -1686,23 +1609,14 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 						k_reproject_hoist4<FMT_RGGB><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 					else
 						k_reproject_hoist4<FMT_GRBG><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
-				} else if (hoist_px == 2) {
+				} else {
+					if ((rc = ensure_hoist_attr(ctx))) return rc;
 					if (p->fmt == VP_FMT_RGGB8)
-						k_reproject_hoist<FMT_RGGB, 2><<<grid, 512, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+						k_reproject_hoist<FMT_RGGB, 4><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
 					else
-						k_reproject_hoist<FMT_GRBG, 2><<<grid, 512, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
-				} else if (p->fmt == VP_FMT_RGGB8)
-					k_reproject_hoist<FMT_RGGB, 4><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
-				else
-					k_reproject_hoist<FMT_GRBG, 4><<<grid, 256, HOIST_SMEM_L, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+						k_reproject_hoist<FMT_GRBG, 4><<<grid, 256, HOIST_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+				}
 				rc = check_launch(ctx, "k_reproject_hoist");
-			} else if (staged) {
-				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), g);
-				if (p->fmt == VP_FMT_RGGB8)
-					k_reproject_staged<FMT_RGGB><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf);
-				else
-					k_reproject_staged<FMT_GRBG><<<grid, 256, 0, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf);
-				rc = check_launch(ctx, "k_reproject_staged");
 			} else if (p->fmt == VP_FMT_BGR8) {
 				SrcBGR src{ raw, p->wq };
 				rc = launch_reproject(ctx, s, src, raw_bytes, p->fmt, p->sample_mode, lut, flat, p->wq, p->hq, (int)nf, g);
@@ -1717,121 +1631,62 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 			Stage st(ctx, "grad_circ", 1, s);
 			CK(ctx, (cudaError_t)launch_grad_circ(s, p->circle_radius, flat, grad, circ, wf, hf, p->grad_offset, seg, g, p->circ_threshold, p->min_score,
 			                                      p->blob_radius, ns, counter, rowcount, masks, wpr, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane]));
-		} else if (sat_free) {
-			Stage st(ctx, "grad_rowscan", 1, s);
-			static const int wide_env = getenv("VP_GRAD_WIDE") ? atoi(getenv("VP_GRAD_WIDE")) : -1; /* tuning aid / A-B */
-			const bool wide = (wide_env >= 0 ? wide_env != 0 : g <= 2) && cdiv(wf, 128) <= ROWWIDE_MAX_WARPS;
-			if (wide) /* one or two frames: a CTA per row, the whole row in flight at once */
-				k_grad_rowscan_wide<float><<<dim3(hf, g), cdiv(wf, 128) * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
-			else
-				k_grad_rowscan<float><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
-			if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
-		} else if (fused_sat) {
-			Stage st(ctx, "grad_sat", 1, s);
-			int* ticket = ctx->sync_words + f0;
-			int* ready = ctx->sync_words + n_frames + (size_t)f0 * n_strips;
-			k_grad_sat<<<dim3(n_strips, g), srows * 32, (size_t)srows * wf * 4, s>>>(flat, grad, sat, wf, hf, p->grad_offset, srows, n_strips, flag, ticket, ready,
-			                                                                      ctx->agg[lane]);
-			if ((rc = check_launch(ctx, "k_grad_sat"))) return rc;
+		} else if (rowsums) {
+			{
+				Stage st(ctx, "grad_rowscan", 1, s);
+				const bool wide = g <= 2 && cdiv(wf, 128) <= ROWWIDE_MAX_WARPS;
+				if (wide) /* one or two frames: a CTA per row, the whole row in flight at once */
+					k_grad_rowscan_wide<float><<<dim3(hf, g), cdiv(wf, 128) * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
+				else
+					k_grad_rowscan<float><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, (float*)rowsum, wf, hf, p->grad_offset, flag);
+				if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
+			}
+			Stage st(ctx, "circ_peaks", 1, s);
+#define VP_CSR(RR)                                                                                                             \
+	case RR: {                                                                                                                 \
+		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
+		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
+		k_circ_stream_rs<RR><<<grid, 128, 0, s>>>((const float*)rowsum, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, \
+		                                          counter, rowcount, masks, wpr, ctx->segsum[lane], ctx->segmax[lane]);         \
+	} break;
+			switch (p->circle_radius) {
+				VP_CSR(1) VP_CSR(2) VP_CSR(3) VP_CSR(4) VP_CSR(5) VP_CSR(6) VP_CSR(7) VP_CSR(8) VP_CSR(9) VP_CSR(10) VP_CSR(11) VP_CSR(12)
+			}
+#undef VP_CSR
+			if ((rc = check_launch(ctx, "k_circ_stream_rs"))) return rc;
 		} else {
+			/* radius outside the specialised range: materialised SAT (exact int32 scans; flagged frames in sequential order),
+			 * unfused circle + count */
 			{
 				Stage st(ctx, "grad_rowscan", 1, s);
 				k_grad_rowscan<int32_t><<<dim3(cdiv(hf, ROWSCAN_WARPS), g), ROWSCAN_WARPS * 32, 0, s>>>(flat, grad, rowsum, wf, hf, p->grad_offset, flag);
 				if ((rc = check_launch(ctx, "k_grad_rowscan"))) return rc;
 			}
 			{
-				Stage st(ctx, "colscan", 1, s);
+				Stage st(ctx, "colscan", 2, s);
 				if ((rc = launch_colscan(ctx, s, rowsum, sat, wf, hf, g, flag))) return rc;
+				k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag);
+				if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
 			}
-		}
-		if (!sat_free) {
-			Stage st(ctx, "sat_fix", 1, s);
-			k_sat_fix<<<g, 1024, 0, s>>>(grad, (float*)rowsum, sat, wf, hf, flag);
-			if ((rc = check_launch(ctx, "k_sat_fix"))) return rc;
-		}
-		if (sat_free) {
-			const int r = p->circle_radius;
-			float* segsum = ctx->segsum[lane];
-			float* segmax = ctx->segmax[lane];
-			if (!use_gc) {
-				Stage st(ctx, "circ_peaks", 1, s);
-#define VP_CSR(RR)                                                                                                             \
-	case RR: {                                                                                                                 \
-		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
-		k_circ_stream_rs<RR><<<grid, 128, 0, s>>>((const float*)rowsum, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, \
-		                                          counter, rowcount, masks, wpr, segsum, segmax);                              \
-	} break;
-				switch (r) {
-					VP_CSR(1) VP_CSR(2) VP_CSR(3) VP_CSR(4) VP_CSR(5) VP_CSR(6) VP_CSR(7) VP_CSR(8) VP_CSR(9) VP_CSR(10) VP_CSR(11) VP_CSR(12)
-				}
-#undef VP_CSR
-				if ((rc = check_launch(ctx, "k_circ_stream_rs"))) return rc;
-			}
-			if (!defer_fallback) {
-				/* the exactness bound of the summed-area table, checked after the fact; frames that left it (or whose row sums
-				 * did) are redone in the reference's sequential order -- two launches that exit at once for every other frame */
-				Stage st(ctx, "sat_check", 2, s);
-				if (use_gc) {
-					CK(ctx, (cudaError_t)launch_sat_check_g(s, grad_circ_check(r, segsum, segmax, ctx->striptot[lane], seg, wf, hf), wf, hf, g, flag));
-					k_fallback_frame<<<g, 1024, 0, s>>>(flat, grad, (float*)rowsum, sat, circ, wf, hf, r, p->circ_threshold, p->min_score, p->blob_radius, ns, flag,
-					                                    counter, rowcount, masks, wpr);
-				} else {
-					k_sat_check_fix<<<g, 1024, 0, s>>>(segsum, segmax, n_seg, grad, (float*)rowsum, sat, wf, hf, flag, counter, rowcount, masks, wpr);
-#define VP_CSF(RR)                                                                                                             \
-	case RR: {                                                                                                                 \
-		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, g);                                                                     \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
-		                                       rowcount, masks, wpr, 1);                                                       \
-	} break;
-					switch (r) {
-						VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
-					}
-#undef VP_CSF
-				}
-				if ((rc = check_launch(ctx, "sat_check/fallback"))) return rc;
-			}
-		} else if (fused_circ) {
-			Stage st(ctx, "circ_peaks", ctx->stream_circ ? 2 : 1, s);
-			if (ctx->stream_circ) {
-				{
-					const int r = p->circle_radius, rr = r < hf / 2 ? r : hf / 2, rcol = r < wf / 2 ? r : wf / 2;
-					const int n_border = 2 * rr * wf + (hf - 2 * rr) * 2 * rcol;
-					if (n_border > 0)
-						k_circ_border<<<dim3(cdiv(n_border, 256), g), 256, 0, s>>>(sat, circ, wf, hf, r, flag);
-				}
-#define VP_CS(RR)                                                                                                              \
-	case RR: {                                                                                                                 \
-		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), cdiv(hf, seg), g);                                                             \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
-		                                       rowcount, masks, wpr, 0);                                                       \
-	} break;
-				switch (p->circle_radius) {
-					VP_CS(1) VP_CS(2) VP_CS(3) VP_CS(4) VP_CS(5) VP_CS(6) VP_CS(7) VP_CS(8) VP_CS(9) VP_CS(10) VP_CS(11) VP_CS(12)
-				}
-#undef VP_CS
-			} else {
-				const dim3 grid(cdiv(wf, CT_W), cdiv(hf, CT_H), g);
-#define VP_CP(RR)                                                                                                              \
-	case RR:                                                                                                                   \
-		k_circ_peaks<RR><<<grid, 256, 0, s>>>(sat, circ, flat, wf, hf, p->circ_threshold, p->min_score, p->blob_radius, ns, flag, counter, \
-		                                      rowcount, masks, wpr);                                                           \
-		break;
-				switch (p->circle_radius) {
-					VP_CP(1) VP_CP(2) VP_CP(3) VP_CP(4) VP_CP(5) VP_CP(6) VP_CP(7) VP_CP(8) VP_CP(9) VP_CP(10) VP_CP(11) VP_CP(12)
-				}
-#undef VP_CP
-			}
-			if ((rc = check_launch(ctx, "k_circ_peaks"))) return rc;
-		} else { /* radius outside the specialised range: unfused circle + count */
 			Stage st(ctx, "circle+count", 2, s);
 			k_circle<<<dim3(cdiv(wf, 64), cdiv(hf, 4), g), 256, 0, s>>>(sat, circ, wf, hf, p->circle_radius);
 			if ((rc = check_launch(ctx, "k_circle"))) return rc;
 			k_peaks_count<<<dim3(cdiv(wf, 256), hf, g), 256, 0, s>>>(flat, circ, wf, hf, p->circ_threshold, p->min_score, p->blob_radius, ns, counter, rowcount,
 			                                                        masks, wpr);
 			if ((rc = check_launch(ctx, "k_peaks_count"))) return rc;
+		}
+		if ((use_gc || rowsums) && !defer_fallback) {
+			/* the exactness bound of the summed-area table, checked after the fact; a frame that left it (or whose row sums did)
+			 * is redone in the reference's sequential order by ONE more launch that exits at once for every other frame */
+			Stage st(ctx, "sat_check", 2, s);
+			if (use_gc)
+				CK(ctx, (cudaError_t)launch_sat_check_g(s, grad_circ_check(p->circle_radius, ctx->segsum[lane], ctx->segmax[lane], ctx->striptot[lane], seg, wf, hf),
+				                                        wf, hf, g, flag));
+			else
+				k_sat_check_rs<<<g, 1024, 0, s>>>(ctx->segsum[lane], ctx->segmax[lane], n_seg, wf, flag);
+			k_fallback_frame<<<g, 1024, 0, s>>>(flat, grad, (float*)rowsum, sat, circ, wf, hf, p->circle_radius, p->circ_threshold, p->min_score, p->blob_radius,
+			                                    ns, flag, counter, rowcount, masks, wpr);
+			if ((rc = check_launch(ctx, "sat_check/fallback"))) return rc;
 		}
 		{
 			Stage st(ctx, "peaks_emit", 1, s);
@@ -1867,32 +1722,15 @@ static int redo_flagged(vp_ctx* ctx, int n_frames, const vp_params* p, uint8_t* 
                         int32_t* d_counter, int* flags)
 {
 	const int wf = p->wf, hf = p->hf, wpr = cdiv(wf, 32);
-	const bool use_gc = ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
-	const int r = p->circle_radius, seg = circ_seg_rows(ctx, wf, hf, n_frames, r, use_gc), n_seg = cdiv(hf, seg);
 	const int ns = need_score(p->circ_threshold, p->min_score);
 	cudaStream_t s = ctx->stream;
 	uint32_t* flat = (uint32_t*)d_flat;
 	float* sat = ctx->sat[0];
 	int rc;
-	Stage st(ctx, "sat_check", use_gc ? 2 : 3, s);
-	if (use_gc) { /* the flags are final: the bound was evaluated next to the record kernel */
-		k_fallback_frame<<<n_frames, 1024, 0, s>>>(flat, d_grad, (float*)ctx->rowsum[0], sat, d_circ, wf, hf, r, p->circ_threshold, p->min_score, p->blob_radius, ns,
-		                                           flags, d_counter, ctx->rowcount, ctx->masks, wpr);
-	} else {
-		k_sat_check_fix<<<n_frames, 1024, 0, s>>>(ctx->segsum[0], ctx->segmax[0], n_seg, d_grad, (float*)ctx->rowsum[0], sat, wf, hf, flags, d_counter, ctx->rowcount,
-		                                          ctx->masks, wpr);
-#define VP_CSF(RR)                                                                                                             \
-	case RR: {                                                                                                                 \
-		constexpr int SWU = 32 - (RR + 2) - 1;                                                                                 \
-		const dim3 grid(cdiv(cdiv(wf, SWU), 4), n_seg, n_frames);                                                              \
-		k_circ_stream<RR><<<grid, 128, 0, s>>>(sat, d_circ, flat, wf, hf, seg, p->circ_threshold, p->min_score, p->blob_radius, ns, flags, d_counter, \
-		                                       ctx->rowcount, ctx->masks, wpr, 1);                                             \
-	} break;
-		switch (r) {
-			VP_CSF(1) VP_CSF(2) VP_CSF(3) VP_CSF(4) VP_CSF(5) VP_CSF(6) VP_CSF(7) VP_CSF(8) VP_CSF(9) VP_CSF(10) VP_CSF(11) VP_CSF(12)
-		}
-#undef VP_CSF
-	}
+	/* the flags are final: the bound was evaluated next to the record kernel */
+	Stage st(ctx, "sat_check", 2, s);
+	k_fallback_frame<<<n_frames, 1024, 0, s>>>(flat, d_grad, (float*)ctx->rowsum[0], sat, d_circ, wf, hf, p->circle_radius, p->circ_threshold, p->min_score,
+	                                           p->blob_radius, ns, flags, d_counter, ctx->rowcount, ctx->masks, wpr);
 	if ((rc = check_launch(ctx, "sat_check/fallback (redo)"))) return rc;
 	return launch_peaks_emit(ctx, s, flat, d_circ, wf, hf, n_frames, p->blob_radius, p->max_blobs, ctx->first_slot, ctx->rowcount, ctx->masks,
 	                         (uint8_t*)d_matches, (size_t)p->max_blobs * 22);
@@ -2090,7 +1928,7 @@ static void lone_fingerprint(vp_ctx* ctx, const HostSlot& s, const vp_params* p,
 	const void* ptrs[18] = { s.raw, s.flat, s.grad, s.circ, s.results, s.results_host, ctx->rowsum[0], ctx->sat[0], ctx->segsum[0], ctx->segmax[0],
 		                     ctx->rowcount, ctx->masks, ctx->first_slot, ctx->flag, lut, tiles, ctx->striptot[0], nullptr };
 	memcpy(fp->ptr, ptrs, sizeof ptrs);
-	const int knobs[10] = { ctx->staged_reproject, ctx->sat_free, ctx->stream_circ, ctx->fused_sat, ctx->hoist_chunk, ctx->group, ctx->lanes, ctx->strips,
+	const int knobs[10] = { ctx->staged_reproject, 0, 0, 0, ctx->hoist_chunk, ctx->group, ctx->lanes, ctx->strips,
 		                    ctx->profiling, ctx->fused_gc };
 	memcpy(fp->knob, knobs, sizeof knobs);
 }

@@ -163,11 +163,8 @@ def load() -> C.CDLL:
         "vp_ctx_set_strips": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_latency_graph": (C.c_int, [vp, C.c_int]),
         "vp_latency_graph_replays": (C.c_uint64, [vp]),
-        "vp_ctx_set_sat_free": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_staged_reproject": (C.c_int, [vp, C.c_int]),
-        "vp_ctx_set_stream_circ": (C.c_int, [vp, C.c_int]),
         "vp_ctx_set_fused_gradcirc": (C.c_int, [vp, C.c_int]),
-        "vp_ctx_set_fused_sat": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
         "vp_detect_last_plan": (C.c_int, [vp, C.POINTER(C.c_int32)]),
         "vp_profiling_enable": (C.c_int, [vp, C.c_int]),
@@ -452,21 +449,12 @@ class Context:
         self._ck(self.lib.vp_ctx_set_group(self.h, n))
 
     def set_staged_reproject(self, on):
-        """0/False = direct gather, 1/True = staged per frame, 2 = staged with the frame-invariant part hoisted (default)."""
+        """0/False = direct gather, 1/True or 2 = shared-memory staged with the frame-invariant part hoisted (default)."""
         self._ck(self.lib.vp_ctx_set_staged_reproject(self.h, int(on)))
-
-    def set_stream_circ(self, on: bool):
-        self._ck(self.lib.vp_ctx_set_stream_circ(self.h, int(on)))
 
     def set_fused_gradcirc(self, on: bool):
         """One gradient + circularity kernel (default) vs gradient + row sums followed by the streaming circularity kernel."""
         self._ck(self.lib.vp_ctx_set_fused_gradcirc(self.h, int(on)))
-
-    def set_fused_sat(self, on: bool):
-        self._ck(self.lib.vp_ctx_set_fused_sat(self.h, int(on)))
-
-    def set_sat_free(self, on: bool):
-        self._ck(self.lib.vp_ctx_set_sat_free(self.h, int(on)))
 
     def set_hoist_chunk(self, n: int):
         self._ck(self.lib.vp_ctx_set_hoist_chunk(self.h, n))
