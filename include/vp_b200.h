@@ -336,7 +336,8 @@ VP_API int vp_ctx_set_strips(vp_ctx* ctx, int strips);
 VP_API int vp_ctx_set_latency_graph(vp_ctx* ctx, int on);
 /* one-frame calls of vp_detect_host served by a graph replay so far (tests, tools) */
 VP_API uint64_t vp_latency_graph_replays(const vp_ctx* ctx);
-/* A/B switch (default on; circle radius 1..12, gradient offset <= 4 and <= (radius+2)/2): gradientDot, the box sums of
+/* A/B switch (0 = never, 1 = default: calls of more than two frames, 2 = also the one- and two-frame calls of the latency path;
+ * circle radius 1..12, gradient offset <= 4 and <= (radius+2)/2): gradientDot, the box sums of
  * satBlobCenter, circularity and peak classification in ONE kernel that reads the flat image once (no row sums, no SAT) vs
  * gradient + row prefix sums followed by the streaming circularity kernel; results are bit-identical */
 VP_API int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on);

@@ -47,12 +47,12 @@ def test_every_circle_radius_single_frame_and_batch(ctx, port, radius, flow):
     wants = [port.detect(f, p) for f in frames]
     assert any(len(w["matches"]) > 0 for w in wants)
     vp = common.to_vp(p)
-    ctx.set_fused_gradcirc(flow == "gradcirc")
+    ctx.set_fused_gradcirc(2 if flow == "gradcirc" else 0)
     try:
         got1 = ctx.detect(frames[0], vp)
         got = common.detect_device(ctx, frames, vp)
     finally:
-        ctx.set_fused_gradcirc(True)
+        ctx.set_fused_gradcirc(1)
     np.testing.assert_array_equal(got1["flat"], wants[0]["flat"])
     np.testing.assert_array_equal(got1["grad"], wants[0]["grad"])
     common.assert_float_images_equal(got1["circ"], wants[0]["circ"])

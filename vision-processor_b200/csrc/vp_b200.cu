@@ -168,7 +168,7 @@ struct vp_ctx {
 	int staged_reproject = 2; /* 0 direct gather, else shared-memory staged with the frame-invariant weights hoisted */
 	int hoist_chunk = 0;      /* frames per CTA of the hoisted kernel; 0 = automatic */
 	int sm_count = 148;
-	bool fused_gc = true; /* gradient + circularity + classification in one kernel (gradcirc.cuh) vs row sums + streaming circularity */
+	int fused_gc = 1; /* gradient + circularity + classification in one kernel (gradcirc.cuh): 0 never, 1 for calls of more than two frames, 2 always */
 	bool gc_attr = false;
 	int32_t* striptot[MAX_LANES] = {}; /* per lane: k_grad_circ's per-row strip sums of gradDot (frames of the group x strips x rows) */
 	size_t striptot_words = 0;
@@ -781,7 +781,6 @@ void vp_ctx_destroy(vp_ctx* c)
 		if (c->strip_uploaded[k]) cudaEventDestroy(c->strip_uploaded[k]);
 	if (c->strip_flat[0]) cudaEventDestroy(c->strip_flat[0]);
 	if (c->lone_fork) cudaEventDestroy(c->lone_fork);
-	for (int l = 0; l < vp_ctx::MAX_LANES; l++)
 	cudaFree(c->rowcount); cudaFree(c->first_slot); cudaFree(c->flag);
 	if (c->flag_host) cudaFreeHost(c->flag_host);
 	c->lone.reset();
@@ -829,7 +828,8 @@ int vp_ctx_set_staged_reproject(vp_ctx* ctx, int on) /* A/B switch: shared-memor
 int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on) /* A/B switch: one gradient + circularity kernel vs row sums + streaming circularity */
 {
 	REQUIRE(ctx, ctx, "ctx is null");
-	ctx->fused_gc = on != 0;
+	REQUIRE(ctx, on >= 0 && on <= 2, "0 = never, 1 = for calls of more than two frames (default), 2 = always");
+	ctx->fused_gc = on;
 	return VP_OK;
 }
 
@@ -1452,7 +1452,11 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 	/* three flows after the reprojection: the fused gradient + circularity kernel (default), gradient + row sums followed by the
 	 * streaming circularity kernel (A/B switch; also gradient offsets the fused kernel does not stage), and -- for radii outside
 	 * the specialised range -- a materialised summed-area table with the unfused circle / count kernels */
-	const bool use_gc = fused_circ && ctx->fused_gc && grad_circ_supported(p->circle_radius, p->grad_offset) && wf <= 8192 && (wf & 1) == 0;
+	/* one or two frames (the latency path of a camera delivering frame by frame) stay with the row-sum flow: its one-CTA-per-row
+	 * gradient kernel and short circularity segments are one memory round trip deep, where the fused kernel walks ~50 rows per
+	 * warp behind its TMA pipeline (p50 0.149 against 0.176 ms, profiles/r02_latency.txt); batches take the fused kernel */
+	const bool use_gc = fused_circ && (ctx->fused_gc == 2 || (ctx->fused_gc == 1 && n_frames > 2)) && grad_circ_supported(p->circle_radius, p->grad_offset) &&
+	                    wf <= 8192 && (wf & 1) == 0;
 	const bool rowsums = fused_circ && !use_gc;
 	const int seg = circ_seg_rows(ctx, wf, hf, n_frames, p->circle_radius, use_gc);
 	const int n_seg = cdiv(hf, seg);

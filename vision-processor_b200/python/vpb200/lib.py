@@ -452,8 +452,9 @@ class Context:
         """0/False = direct gather, 1/True or 2 = shared-memory staged with the frame-invariant part hoisted (default)."""
         self._ck(self.lib.vp_ctx_set_staged_reproject(self.h, int(on)))
 
-    def set_fused_gradcirc(self, on: bool):
-        """One gradient + circularity kernel (default) vs gradient + row sums followed by the streaming circularity kernel."""
+    def set_fused_gradcirc(self, on):
+        """One gradient + circularity kernel vs gradient + row sums followed by the streaming circularity kernel: 0/False never,
+        1/True for calls of more than two frames (default), 2 also for the one- and two-frame calls of the latency path."""
         self._ck(self.lib.vp_ctx_set_fused_gradcirc(self.h, int(on)))
 
     def set_hoist_chunk(self, n: int):
