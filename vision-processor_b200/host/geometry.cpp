@@ -180,45 +180,70 @@ int vp_geometry_check(const vp_camera_model* model, const vp_field_size* field, 
 	float min_scale = std::numeric_limits<float>::max(), max_scale = 0.f, sum = 0.f;
 	long long n = 0;
 	const float lim_x = field->field_length / 2.f + goal_boundary, lim_y = field->field_width / 2.f + field->boundary_width;
-	/* The positions (one image2field per pixel, ~35 ns each: 43 ms for 1224x1024 on one core) are independent and computed by all
-	 * host threads; the SUM stays one fp32 variable fed in raster order, exactly like the reference's loop -- past 2^23 every
-	 * dx + dy is absorbed with a rounding error that depends on that order. */
+	/* The field position of every pixel (one image2field each) and the neighbour distances dx + dy derived from them are
+	 * independent and computed by all host threads; minimum, maximum and count do not depend on the order either.  The SUM stays
+	 * one fp32 variable fed in raster order, exactly like the reference's loop -- past 2^23 every dx + dy is absorbed with a
+	 * rounding error that depends on that order.  43 ms -> a few ms for 1224x1024 on 16 cores. */
 	std::vector<float> pos((size_t)2 * width * height);
-	{
-		const unsigned hw = std::thread::hardware_concurrency();
-		const int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, std::min(16u, (unsigned)height / 64u + 1u)));
-		auto fill = [&](int y0, int y1) {
-			float p[3];
-			for (int y = y0; y < y1; y++)
-				for (int x = 0; x < width; x++) {
-					image2field(m, (float)x, (float)y, h, p);
-					pos[((size_t)y * width + x) * 2] = p[0];
-					pos[((size_t)y * width + x) * 2 + 1] = p[1];
-				}
-		};
+	std::vector<float> dist((size_t)width * height); /* dx + dy of pixel (x, y), or -1 where the pixel does not count */
+	const unsigned hw = std::thread::hardware_concurrency();
+	const int n_threads = (int)std::max(1u, std::min(hw ? hw : 1u, std::min(16u, (unsigned)height / 64u + 1u)));
+	auto in_parallel = [&](auto&& body) {
 		std::vector<std::thread> pool;
 		for (int t = 1; t < n_threads; t++)
-			pool.emplace_back(fill, (int)((long long)height * t / n_threads), (int)((long long)height * (t + 1) / n_threads));
-		fill(0, (int)((long long)height * 1 / n_threads));
+			pool.emplace_back(body, t, (int)((long long)height * t / n_threads), (int)((long long)height * (t + 1) / n_threads));
+		body(0, 0, (int)((long long)height * 1 / n_threads));
 		for (std::thread& t : pool)
 			t.join();
-	}
-	float tmp[3];
-	for (int y = 0; y < height - 1; y++) {
-		const float* cur = &pos[(size_t)y * width * 2];
-		const float* nxt = cur + (size_t)width * 2;
-		for (int x = 0; x < width - 1; x++) {
-			const float px = cur[2 * x], py = cur[2 * x + 1];
-			if (std::fabs(px) < lim_x && std::fabs(py) < lim_y) { /* false for NaN, as in the reference */
-				const float dx = norm2(cur[2 * x + 2] - px, cur[2 * x + 3] - py);
-				const float dy = norm2(nxt[2 * x] - px, nxt[2 * x + 1] - py);
-				min_scale = std::fmin(min_scale, std::fmin(dx, dy));
-				max_scale = std::fmax(max_scale, std::fmax(dx, dy));
-				sum += dx + dy;
-				n += 2;
+	};
+	in_parallel([&](int, int y0, int y1) {
+		float p[3];
+		for (int y = y0; y < y1; y++)
+			for (int x = 0; x < width; x++) {
+				image2field(m, (float)x, (float)y, h, p);
+				pos[((size_t)y * width + x) * 2] = p[0];
+				pos[((size_t)y * width + x) * 2 + 1] = p[1];
+			}
+	});
+	std::vector<float> t_min(n_threads, std::numeric_limits<float>::max()), t_max(n_threads, 0.f);
+	std::vector<long long> t_n(n_threads, 0);
+	in_parallel([&](int t, int y0, int y1) {
+		float mn = std::numeric_limits<float>::max(), mx = 0.f;
+		long long cnt = 0;
+		for (int y = y0; y < std::min(y1, height - 1); y++) {
+			const float* cur = &pos[(size_t)y * width * 2];
+			const float* nxt = cur + (size_t)width * 2;
+			float* d = &dist[(size_t)y * width];
+			for (int x = 0; x < width - 1; x++) {
+				const float px = cur[2 * x], py = cur[2 * x + 1];
+				d[x] = -1.f;
+				if (std::fabs(px) < lim_x && std::fabs(py) < lim_y) { /* false for NaN, as in the reference */
+					const float dx = norm2(cur[2 * x + 2] - px, cur[2 * x + 3] - py);
+					const float dy = norm2(nxt[2 * x] - px, nxt[2 * x + 1] - py);
+					mn = std::fmin(mn, std::fmin(dx, dy));
+					mx = std::fmax(mx, std::fmax(dx, dy));
+					const float v = dx + dy;
+					d[x] = v >= 0.f ? v : std::numeric_limits<float>::quiet_NaN(); /* a NaN distance still counts (and poisons the sum) */
+					cnt += 2;
+				}
 			}
 		}
+		t_min[t] = mn;
+		t_max[t] = mx;
+		t_n[t] = cnt;
+	});
+	for (int t = 0; t < n_threads; t++) {
+		min_scale = std::fmin(min_scale, t_min[t]);
+		max_scale = std::fmax(max_scale, t_max[t]);
+		n += t_n[t];
 	}
+	for (int y = 0; y < height - 1; y++) { /* Perspective.cpp:78-91: one running fp32 sum, raster order */
+		const float* d = &dist[(size_t)y * width];
+		for (int x = 0; x < width - 1; x++)
+			if (!(d[x] < 0.f))
+				sum += d[x];
+	}
+	float tmp[3];
 	g.field_scale = sum / (float)n * resampling_factor; /* 0/0 = NaN when no pixel sees the field, as in the reference */
 	g.min_field_scale = min_scale;
 	g.max_field_scale = max_scale;
