@@ -8,11 +8,17 @@ import os
 import subprocess
 import sys
 
-STAGE = {"k_reproject_hoist4": "reproject", "k_reproject_hoist": "reproject", "k_reproject_staged": "reproject", "k_grad_rowscan": "grad_rowscan", "k_colscan": "colscan",
-         "k_circ_stream_rs": "circ_peaks", "k_peaks_emit": "peaks_emit", "k_sat_check_fix": "sat_check", "k_peaks_prepare": "prepare"}
+STAGE = {"k_reproject_hoist4": "reproject", "k_reproject_hoist": "reproject", "k_grad_circ": "grad_circ", "k_grad_rowscan": "grad_rowscan", "k_colscan": "colscan",
+         "k_circ_stream_rs": "circ_peaks", "k_peaks_emit": "peaks_emit", "k_sat_check_g": "sat_check", "k_sat_check_rs": "sat_check", "k_fallback_frame": "sat_check",
+         "k_peaks_prepare": "prepare"}
 frames, reps = float(sys.argv[1]), sys.argv[2:]
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
-res = {"sources": [os.path.basename(r) for r in reps], "frames_per_launch": frames, "kernels": {}}
+try:
+    sha = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=os.path.dirname(dst)).stdout.strip()
+except Exception:  # noqa: BLE001
+    sha = "?"
+res = {"sources": [os.path.basename(r) for r in reps], "source": "ncu --set full of tools/prof_step.py, " + ", ".join(os.path.basename(r) for r in reps) + ", tree " + sha,
+       "frames_per_launch": frames, "kernels": {}}
 h, units = [], []
 
 
@@ -31,7 +37,7 @@ for rep in reps:
   for r in rows[2:]:
     name = r[h.index("Kernel Name")]
     for k, st in STAGE.items():
-        if (k + "(" in name or k + "<" in name) and st not in seen:
+        if (k + "(" in name or k + "<" in name) and (st not in seen or st == "sat_check"):
             rd, wr = col(r, "dram__bytes_read.sum"), col(r, "dram__bytes_write.sum")
             e = res["kernels"].setdefault(st, {"kernel": k, "dram_bytes_per_frame": 0.0, "us_per_frame_under_ncu": 0.0})
             e["dram_bytes_per_frame"] += (rd + wr) / frames
