@@ -90,6 +90,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
 	             : "memory");
 }
 
+/* true in exactly one lane of a converged warp (ELECT): what follows is issued once, with operands ptxas may keep uniform */
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t pred;
+	asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+	return pred != 0;
+}
+
 __device__ __forceinline__ uint2 lds64(const uint32_t* p)
 {
 	uint2 v;
@@ -167,9 +175,7 @@ __device__ __forceinline__ uint32_t lds32a(uint32_t addr)
 template <class T>
 __device__ __forceinline__ T* bump(T* p, unsigned bytes)
 {
-	unsigned long long r;
-	asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(bytes), "l"(p));
-	return reinterpret_cast<T*>(r);
+	return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + bytes);
 }
 
 /* Ring of staged flat rows of one warp: three slots of D rows and a mirror slot below them.  Group g (gradient rows t .. t+D-1)
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		if (bulk) {
 			uint64_t* bar = bars + (n & 1);
 			if (first >= 0 && first + D <= h) { /* the common case: one tensor copy, issued by one lane */
-				if (lane == 0) {
+				if (elect_one()) {
 					mbar_expect_tx(bar, (uint32_t)(twice ? 2 : 1) * D * RB);
 					tensor_copy_g2s(dst, &tmap, xl, first, f, bar);
 					if (twice)
@@ -299,9 +305,14 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	int strip_run = 0; /* sum of gradDot over the strip's own columns and the segment's rows so far (warp-uniform, exact) */
 	const int t0 = ys - 1 - R;
 	const int n_groups = (ye + R - t0 + D) / D; /* whole groups: the extra rows of the last one are computed and never used */
+	/* groups g_lo .. g_hi-1 are FAST: gradient rows t .. t+D-1 and output rows t-R .. t-R+D-1 all inside [ys, ye) (hence inside
+	 * [1, h-1]), t = t0 + g D: t - R >= ys <=> g D >= 2R + 1, t + D <= ye <=> (g + 1) D <= ye - t0 */
+	const int g_lo = cols_free ? (2 * R + 1 + D - 1) / D : 0;
+	const int g_hi = cols_free ? (ye - t0) / D : 0;
 	/* output pointers of this lane's column pair, advanced row by row: gradDot row tau and circularity row y = tau - R */
-	float* pg = grad + fbase + ((ptrdiff_t)t0 * w + c0);
-	float* pc = circ_out + fbase + ((ptrdiff_t)(t0 - R) * w + c0);
+	char* const gbase = reinterpret_cast<char*>(grad + fbase + (ptrdiff_t)t0 * w);          /* warp-uniform bases (may lie before the */
+	char* const cbase = reinterpret_cast<char*>(circ_out + fbase + (ptrdiff_t)(t0 - R) * w); /* buffer: only owned rows are stored)    */
+	unsigned off = (unsigned)c0 * 4u; /* ONE 32-bit byte offset for both stores, advanced by a row per step (<= (seg + 3R + D) rows x w x 4 < 2^32) */
 
 	/* One group = D gradient rows tau = t .. t+D-1, straight-line code.  Step s finishes window row v = tau-K and the
 	 * circularity row y = tau-R.  FAST groups (every row owned by the segment both as a gradient row and as an output row,
@@ -340,8 +351,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 			const float2 gf = add2(make_float2(__int_as_float(g0 + 0x4B400000), __int_as_float(g1 + 0x4B400000)), make_float2(-12582912.0f, -12582912.0f));
 			const bool own_row = FAST || (tau >= ys && tau < ye);
 			if (out_lane && own_row)
-				*reinterpret_cast<float2*>(pg) = gf;
-			pg = bump(pg, w4);
+				*reinterpret_cast<float2*>(gbase + off) = gf;
 			if (own_row) { /* what the exactness bound of the SAT is made of: the strip's running sum after every row (one warp reduction) ... */
 				strip_run += __reduce_add_sync(0xffffffffu, out_lane ? g0 + g1 : 0);
 				if (lane == s)
@@ -378,8 +388,8 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 			const int y = y0 + s;
 			crow[s + 2] = c;
 			if (out_lane && (FAST || (y >= ys && y < ye)))
-				*reinterpret_cast<float2*>(pc) = c;
-			pc = bump(pc, w4);
+				*reinterpret_cast<float2*>(cbase + off) = c;
+			off += w4;
 		}
 		c_prev2 = crow[D];
 		c_prev1 = crow[D + 1];
@@ -391,17 +401,10 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		for (int s = 2; s <= D; s++)
 			mx = fmaxf(mx, fmaxf(crow[s].x, crow[s].y));
 		if (__any_sync(0xffffffffu, out_lane && !(mx < thr))) {
-#pragma unroll 1
-			for (int i = 1; i <= D; i++) {
-				const int yy = y0 + i - 2;
-				float2 cm = crow[1], up = crow[0], dn = crow[2];
 #pragma unroll
-				for (int k = 2; k <= D; k++)
-					if (i == k) {
-						cm = crow[k];
-						up = crow[k - 1];
-						dn = crow[k + 1];
-					}
+			for (int i = 1; i <= D; i++) { /* unrolled: the rows stay where they are, a row without a candidate costs a compare and a vote */
+				const int yy = y0 + i - 2;
+				const float2 cm = crow[i], up = crow[i - 1], dn = crow[i + 1];
 				const bool rows_in = yy >= ys && yy < ye;
 				const bool cand_a = out_lane && rows_in && !(cm.x < thr), cand_b = out_lane && rows_in && !(cm.y < thr);
 				if (!__any_sync(0xffffffffu, cand_a || cand_b))
@@ -431,8 +434,7 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 		const int next = slot == 2 ? 0 : slot + 1;
 		if (g + 1 < n_groups)
 			stage_group(t + D + o, next, g + 2);
-		/* gradient rows t .. t+D-1 and output rows t-R .. t-R+D-1 all inside [ys, ye) (hence inside [1, h-1]) */
-		if (cols_free && t - R >= ys && t + D <= ye)
+		if (g >= g_lo && g < g_hi)
 			group(IntC<1>{}, g, slot);
 		else
 			group(IntC<0>{}, g, slot);
