@@ -700,6 +700,33 @@ constexpr size_t HOIST4_SMEM = HOIST4_TBUF * (size_t)HT * 4 + HOIST4_STAGES * 4 
 constexpr float HOIST4_WSCALE = VP_HOIST4_DENORM ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
 constexpr float HOIST4_ROUND = VP_HOIST4_DENORM ? 1.4901161193847656e-08f /* 2^23 * 2^-49 = 2^-26 */ : 8388608.0f;
 
+/* build-time A/B: the integer tail of resampling.cl:82-91 (green = mean of the two green planes, dRGB = (2x - y - z + 510) >> 2,
+ * packed RGBA) for TWO frames at once in the 16-bit halves of a register (default), or frame by frame on the biased words.
+ * The rounded sums leave bias + n with n <= 255 in the low mantissa bits, so PRMT packs (n of frame A, n of frame B); all of the
+ * tail is integer arithmetic mod 2^32 on A + 2^16 B whose final per-lane values (2x - y - z + 510) * 64 lie in [0, 65280]:
+ * whatever an intermediate borrows from or carries into the other lane is returned by the end.  The factor 64 puts the
+ * quotient's eight bits (bits 2..9) into byte 1 of each lane, where PRMT picks them up -- no shifts, no masks.
+ * 17 instructions per frame pair against 14 per frame. */
+#ifndef VP_HOIST4_PAIRTAIL
+#define VP_HOIST4_PAIRTAIL 1
+#endif
+/* build-time A/B: the three sums of a channel as FADD2.FTZ (1, see add2_ftz) or as FFMA2 with an opaque 1.0 (0) */
+#ifndef VP_HOIST4_FTZADD
+#define VP_HOIST4_FTZADD 1
+#endif
+__device__ __forceinline__ void drgb_biased_pair(float2 r, float2 g1, float2 g2, float2 b, uint32_t& px_a, uint32_t& px_b)
+{
+	const uint32_t R = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x5410), B = __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x5410);
+	const uint32_t G1 = __byte_perm(__float_as_uint(g1.x), __float_as_uint(g1.y), 0x5410), G2 = __byte_perm(__float_as_uint(g2.x), __float_as_uint(g2.y), 0x5410);
+	const uint32_t G = ((G1 & 0xFFFEFFFEu) + (G2 & 0xFFFEFFFEu)) >> 1; /* (g1 >> 1) + (g2 >> 1) in each lane: the sum is even, no bit crosses */
+	const uint32_t t = 510u * 64u * 0x00010001u - (R + G + B) * 64u;
+	const uint32_t dr = R * 192u + t, dg = G * 192u + t, db = B * 192u + t; /* (3x - s + 510) << 6 */
+	const uint32_t rg = __byte_perm(dr, dg, 0x7351);           /* dr A, dg A, dr B, dg B */
+	const uint32_t ba = __byte_perm(db, 0xFFFFFFFFu, 0x4341);  /* db A, 255, db B, 255 */
+	px_a = __byte_perm(rg, ba, 0x5410);
+	px_b = __byte_perm(rg, ba, 0x7632);
+}
+
 /* w * (byte LO, byte LO+1) of a staged word, two frames at once; bit for bit mul.rn(w, float(b)) (times 2^-49 in variant 1) */
 template <int LO>
 __device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w, float wm)
@@ -720,6 +747,8 @@ template <int FMT, bool FULL>
 __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][VP_HOIST4_AXES ? 4 : 8], const int (&O)[4][4], uint32_t* __restrict__ out,
                                              uint32_t nfl, int wf, bool okx, int rows_ok, int n_valid, unsigned long long one2)
 {
+	const size_t nfl4 = (size_t)nfl * 4, wf4 = (size_t)wf * 4;
+	(void)nfl4; (void)wf4;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		float2 ab[4], cd[4]; /* channel c: (frame A, frame B) and (frame C, frame D) */
@@ -749,14 +778,40 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 				const float2 pab = weighted_pair<0>(wd, w, wm);
 				const float2 pcd = weighted_pair<2>(wd, w, wm);
 				/* ((p00 + p10) + p01) + p11, every sum rounded on its own */
+#if VP_HOIST4_FTZADD
+				ab[c] = tap == 0 ? pab : add2_ftz(pab, ab[c]);
+				cd[c] = tap == 0 ? pcd : add2_ftz(pcd, cd[c]);
+#else
 				ab[c] = tap == 0 ? pab : add2_opaque(pab, ab[c], one2);
 				cd[c] = tap == 0 ? pcd : add2_opaque(pcd, cd[c], one2);
+#endif
 			}
 			ab[c] = add2(ab[c], make_float2(HOIST4_ROUND, HOIST4_ROUND)); /* RNE to integer in the mantissa */
 			cd[c] = add2(cd[c], make_float2(HOIST4_ROUND, HOIST4_ROUND));
 		}
-		uint32_t* o = out + (uint32_t)(4 * k) * (uint32_t)wf;
 		const bool in = FULL || (okx && 4 * k < rows_ok);
+#if VP_HOIST4_PAIRTAIL
+		/* the store address walks frame by frame and then to the next row with 64-bit ADDS (IADD3 + IADD3.X: the cheap integer
+		 * path) instead of a scaled 64-bit address per store (LEA + LEA.HI.X on the ALU pipe that the PRMTs saturate) */
+		unsigned char* o = reinterpret_cast<unsigned char*>(out) + (size_t)(4 * k) * wf4;
+		/* the integer tail for two frames at once in 16-bit lanes */
+		constexpr int CR = FMT == FMT_RGGB ? 0 : 1, CG1 = FMT == FMT_RGGB ? 1 : 0, CG2 = FMT == FMT_RGGB ? 2 : 3, CB = FMT == FMT_RGGB ? 3 : 2;
+#pragma unroll
+		for (int j = 0; j < 4; j += 2) {
+			uint32_t pa, pb;
+			if (j == 0)
+				drgb_biased_pair(ab[CR], ab[CG1], ab[CG2], ab[CB], pa, pb);
+			else
+				drgb_biased_pair(cd[CR], cd[CG1], cd[CG2], cd[CB], pa, pb);
+			if (in && j < n_valid)
+				*reinterpret_cast<uint32_t*>(o) = pa;
+			o += nfl4;
+			if (in && j + 1 < n_valid)
+				*reinterpret_cast<uint32_t*>(o) = pb;
+			o += nfl4;
+		}
+#else
+		uint32_t* o = out + (uint32_t)(4 * k) * (uint32_t)wf;
 #pragma unroll
 		for (int j = 0; j < 4; j++) {
 			uint32_t v[4];
@@ -767,6 +822,7 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 			if (in && j < n_valid)
 				o[(size_t)j * nfl] = px;
 		}
+#endif
 	}
 }
 
