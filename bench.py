@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -55,10 +56,15 @@ def metric_name(w, h):
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def build_workload(sensor_w: int, sensor_h: int, n_distinct: int, cam_seed: int = 0):
-    """The synthetic camera of SURVEY 8(d) + n_distinct noisy frames of one rendered SSL scene."""
+def build_workload(sensor_w: int, sensor_h: int, n_distinct: int, cam_seed: int = 0, k2: float = 0.0, tilt: float = 0.0):
+    """The synthetic camera of SURVEY 8(d) + n_distinct noisy frames of one rendered SSL scene.  k2 / tilt: the stress camera of
+    SURVEY 8(d) (radial distortion, rotation about the x axis in rad) instead of the undistorted top-down one."""
     wq, hq = sensor_w // 2, sensor_h // 2
-    cam = G.default_camera(wq, hq, k2=0.0)
+    cam = G.default_camera(wq, hq, k2=k2)
+    if tilt:
+        c, s_ = math.cos(tilt / 2), math.sin(tilt / 2)
+        cam = G.CameraModel(size=(wq, hq), focal_length=float(wq), principal_point=(wq / 2.0, hq / 2.0), distortion_k2=k2,
+                            pos=(0.0, 0.0, 5000.0), quat_wxyz=(s_, -c, 0.0, 0.0))
     persp = G.Perspective(cam)
     persp.geometry_check(wq, hq, 180.0)
     lp = G.launch_params(persp, S.FMT_RGGB, wq, hq)
@@ -76,6 +82,7 @@ def workload_config(args, lp, world: int) -> dict:
     return {"workload": CONFIGS[args.config]["what"] if not args.frame_size else f"{w}x{h} BayerRG8 full detection pipeline; one stream per GPU",
             "config_id": args.config, "frame_size": [w, h], "flat_size": [lp.wf, lp.hf], "max_blobs": lp.max_blobs,
             "circle_radius": lp.circle_radius, "grad_offset": lp.grad_offset,
+            "camera": {"k2": args.k2, "tilt_rad": args.tilt},
             "frames_in_ring_per_gpu": args.batch,
             "l2": f"inputs larger than L2: a ring of {args.batch} frames x {rb} B = {args.batch * rb / 1e6:.0f} MB raw per GPU, streamed from HBM on every pass"
                   if args.batch * rb > 126e6 else
@@ -187,7 +194,7 @@ def cpu_baseline(args, lp, frames, budget_s: float = 12.0) -> dict:
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
-    lp, frames = build_workload(*args.size, 4)
+    lp, frames = build_workload(*args.size, 4, k2=args.k2, tilt=args.tilt)
     O, orc, kind = cpu_pipeline()
     cores = os.cpu_count() or 1
     orc.set_threads(cores)
@@ -255,6 +262,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--frame-size", default="", help="WxH of the Bayer sensor (overrides the size of --config)")
+    ap.add_argument("--k2", type=float, default=0.0, help="radial distortion of the synthetic camera (SURVEY 8(d) stress case: 0.12)")
+    ap.add_argument("--tilt", type=float, default=0.0, help="rotation of the synthetic camera about the x axis in rad (stress case: 0.2)")
     ap.add_argument("--batch", type=int, default=0, help="frames in the device-resident ring per GPU (0 = the config's default: three groups of 64 frames on three streams)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the K timed steps last at least this long (passes per step are scaled up)")
     ap.add_argument("--e2e-batch", type=int, default=32)
@@ -310,7 +319,7 @@ def main():
 
     # ---- workload: camera `rank` of the field, a ring of B frames ---------------------------------
     n_distinct = 8 if args.size[0] * args.size[1] <= 6e6 else 4
-    lp, frames = build_workload(*args.size, n_distinct, cam_seed=rank)
+    lp, frames = build_workload(*args.size, n_distinct, cam_seed=rank, k2=args.k2, tilt=args.tilt)
     p = lib.params_from_launch(lp)
     B, nf, nq, rb = args.batch, lp.wf * lp.hf, lp.wq * lp.hq, frames.shape[1]
     dev = torch.device("cuda", local_rank)
@@ -465,7 +474,8 @@ def main():
     frames_per_step = B * passes
     value = world * frames_per_step * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- the same pass with a CUDA event pair around every kernel (per-kernel durations; one stream) ----
+    # ---- the same pass with a CUDA event pair around every kernel; the library runs a profiled call on ONE stream, so a kernel's
+    # duration is its own (the three-stream pipeline above overlaps them: the durations add up to more than its step) ----
     ctx.profiling(True)
     one_pass()
     ctx.sync()
@@ -544,7 +554,7 @@ def main():
         "dtype": "u8/int32/f32", "data": "synthetic",
         "config": workload_config(args, lp, world),
         "run": {"passes_per_step": passes, "frames_per_step_per_gpu": frames_per_step, "timed_seconds": elapsed_ms * 1e-3, "blobs_per_frame": blobs_per_frame,
-                "plan": plan, "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else "all",
+                "plan": plan, "reprojection_tiles": ctx.tile_stats(p), "host_cpus_of_rank0": len(numa_cpus) if numa_cpus else "all",
                 "note": "a step = passes_per_step passes of vp_detect_batch_device over the device-resident ring; every frame of every pass is counted"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_frames_per_step * rb, "d2h_bytes_per_step": e2e_frames_per_step * (p.max_blobs * 22 + 12),

@@ -348,6 +348,11 @@ VP_API int vp_ctx_set_fused_gradcirc(vp_ctx* ctx, int on);
  * radii outside 1..12, 3 row sums + streaming circularity, 4 fused gradient + circularity), plan[5] rows per
  * circularity segment, plan[6], plan[7] reserved */
 VP_API int vp_detect_last_plan(const vp_ctx* ctx, int32_t plan[8]);
+/* how the geometry of `p` maps onto the staged reprojection (resampling.cl:52-99 on the fused path): stats[0] = 64x16 flat tiles
+ * per frame, stats[1] = tiles whose raw footprint fits the staged planes (the rest fall back to the per-pixel gather: strong
+ * distortion or tilt), stats[2] = tiles staged with 16-byte vectors, stats[3] = largest number of staged quad rows of a tile.
+ * Builds (and caches) the geometry tables like a detection call would; blocks until they are there. */
+VP_API int vp_tile_stats(vp_ctx* ctx, const vp_params* p, int32_t stats[4]);
 
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 VP_API uint64_t vp_launch_count(const vp_ctx* ctx);

@@ -212,6 +212,17 @@ def test_full_size_distorted_tilted_camera_through_the_four_frame_kernel(ctx, po
     assert got["plan"]["reproject"] == 4 and got["plan"]["group"] == 6
     for i in (0, 4, 5):
         common.assert_frame_equal(got, i, port.detect(frames[i], p))
+    # the staged kernel really carried this camera: vp_tile_stats counts the tiles whose footprint fits the staged planes
+    st = ctx.tile_stats(common.to_vp(p))
+    assert st["tiles"] == -(-p.wf // 64) * -(-p.hf // 16) and 0 < st["staged"] <= st["tiles"] and st["max_rows"] <= 24
+    assert st["staged"] >= 0.9 * st["tiles"], st
+
+
+def test_tile_stats_of_the_headline_camera(ctx):
+    """The undistorted top-down camera of the benchmark: every tile is staged, with 16-byte vectors (2448 % 16 == 0)."""
+    p, _ = full_size_case(2448, 2048, n_frames=1)
+    st = ctx.tile_stats(common.to_vp(p))
+    assert st["tiles"] == 20 * 64 and st["staged"] == st["tiles"] and st["vectorised"] == st["tiles"], st
 
 
 def test_misaligned_device_pointers_are_refused_not_faulted(ctx):

@@ -28,7 +28,7 @@ ap.add_argument("--no-graph", action="store_true", help="direct launches instead
 ap.add_argument("--ring", type=int, default=4, help="pinned frame buffers the calls rotate through (1 = always the same address)")
 args = ap.parse_args()
 
-lp, frames = bench.build_workload(4)
+lp, frames = bench.build_workload(2448, 2048, 4)
 args.ring = max(1, min(args.ring, 32))
 p = lib.params_from_launch(lp)
 rb = p.raw_frame_bytes()

@@ -801,6 +801,30 @@ int vp_ctx_sync(vp_ctx* ctx)
 
 void* vp_ctx_stream(vp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+int vp_tile_stats(vp_ctx* ctx, const vp_params* p, int32_t stats[4])
+{
+	REQUIRE(ctx, ctx && p && stats, "null argument");
+	REQUIRE(ctx, p->wq > 0 && p->hq > 0 && p->wf > 0 && p->hf > 0, "empty geometry");
+	const float2* lut;
+	const TileEntry* tiles;
+	int rc = get_lut(ctx, &p->model, p->max_robot_height, p->field_scale, p->off_x, p->off_y, p->wf, p->hf, p->wq, p->hq, &lut, &tiles);
+	if (rc != VP_OK)
+		return rc;
+	const int n = cdiv(p->wf, FT_W) * cdiv(p->hf, FT_H);
+	std::vector<TileEntry> host((size_t)n);
+	CK(ctx, cudaMemcpyAsync(host.data(), tiles, host.size() * sizeof(TileEntry), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(ctx, cudaStreamSynchronize(ctx->stream));
+	stats[0] = n;
+	stats[1] = stats[2] = stats[3] = 0;
+	for (const TileEntry& e : host) {
+		stats[1] += e.flags & 1;
+		stats[2] += (e.flags & 3) == 3;
+		if ((e.flags & 1) && e.height > stats[3])
+			stats[3] = e.height;
+	}
+	return VP_OK;
+}
+
 int vp_detect_last_plan(const vp_ctx* ctx, int32_t plan[8])
 {
 	if (!ctx || !plan)

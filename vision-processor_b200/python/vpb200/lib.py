@@ -167,6 +167,7 @@ def load() -> C.CDLL:
         "vp_ctx_set_fused_gradcirc": (C.c_int, [vp, C.c_int]),
         "vp_launch_count": (C.c_uint64, [vp]),
         "vp_detect_last_plan": (C.c_int, [vp, C.POINTER(C.c_int32)]),
+        "vp_tile_stats": (C.c_int, [vp, C.POINTER(Params), C.POINTER(C.c_int32)]),
         "vp_profiling_enable": (C.c_int, [vp, C.c_int]),
         "vp_profiling_count": (C.c_int, [vp]),
         "vp_profiling_get": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
@@ -465,6 +466,12 @@ class Context:
         a = (C.c_int32 * 8)()
         self._ck(self.lib.vp_detect_last_plan(self.h, a))
         return dict(reproject=a[0], chunk=a[1], group=a[2], lanes=a[3], circ=a[4], seg_rows=a[5], tma=a[6])
+
+    def tile_stats(self, p) -> dict:
+        """How the geometry maps onto the staged reprojection (vp_tile_stats): tiles per frame, tiles that fit the staged planes."""
+        a = (C.c_int32 * 4)()
+        self._ck(self.lib.vp_tile_stats(self.h, C.byref(p), a))
+        return dict(tiles=a[0], staged=a[1], vectorised=a[2], max_rows=a[3])
 
     def set_strips(self, n: int):
         """Chunks the upload of a lone frame is cut into on the latency path of detect_host (1 = no overlap)."""
