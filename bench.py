@@ -44,8 +44,8 @@ from vpb200 import geometry as G, synth as S  # noqa: E402
 
 UNIT = "frames/s"
 CONFIGS = {
-    2: dict(size=(2448, 2048), batch=192, what="single camera 2448x2048 BayerRG8 full detection pipeline (BASELINE configs[1]); one camera stream per GPU"),
-    4: dict(size=(2448, 2048), batch=192, what="2448x2048 BayerRG8 full detection + one NV12 debug-stream view per frame, views rotated as main.cpp:380-393 "
+    2: dict(size=(2448, 2048), batch=384, what="single camera 2448x2048 BayerRG8 full detection pipeline (BASELINE configs[1]); one camera stream per GPU"),
+    4: dict(size=(2448, 2048), batch=384, what="2448x2048 BayerRG8 full detection + one NV12 debug-stream view per frame, views rotated as main.cpp:380-393 "
                                                "(BASELINE configs[3]); one camera stream per GPU"),
     5: dict(size=(4096, 3000), batch=64, what="batched 4096x3000 BayerRG8 full detection (BASELINE configs[4]); one batch stream per GPU"),
 }
@@ -264,7 +264,7 @@ def main():
     ap.add_argument("--frame-size", default="", help="WxH of the Bayer sensor (overrides the size of --config)")
     ap.add_argument("--k2", type=float, default=0.0, help="radial distortion of the synthetic camera (SURVEY 8(d) stress case: 0.12)")
     ap.add_argument("--tilt", type=float, default=0.0, help="rotation of the synthetic camera about the x axis in rad (stress case: 0.2)")
-    ap.add_argument("--batch", type=int, default=0, help="frames in the device-resident ring per GPU (0 = the config's default: three groups of 64 frames on three streams)")
+    ap.add_argument("--batch", type=int, default=0, help="frames in the device-resident ring per GPU (0 = the config's default: three groups of 128 frames on three streams)")
     ap.add_argument("--min-seconds", type=float, default=1.0, help="the K timed steps last at least this long (passes per step are scaled up)")
     ap.add_argument("--e2e-batch", type=int, default=32)
     ap.add_argument("--group", type=int, default=0, help="frames per launch group (0 = automatic)")

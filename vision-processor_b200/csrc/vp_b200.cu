@@ -634,13 +634,15 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 {
 	if (ctx->group > 0)
 		return ctx->group < n_frames ? ctx->group : n_frames;
-	/* Measured on B200 (profiles/r01_group_sweep.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels over a
-	 * few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set
-	 * has left the 126 MB L2; ~40 Mpx per launch is on the plateau, ~80 Mpx another 2 % up with the final kernels.  Three lanes (streams) with one group each in flight
-	 * cover the launch gaps and tails of one group with the other groups' kernels (profiles/r01_group_sweep.txt). */
-	size_t g = (size_t)80 * 1024 * 1024 / nf; /* 64 frames of 1224x1024: 10.44 us/frame against 10.61 at 32 (profiles/r01_group_sweep.txt) */
+	/* Measured on B200 (profiles/r01_group_sweep.txt, r02_sweeps.txt): a 1.25 Mpx frame is ~4 pixels per resident thread, so kernels
+	 * over a few frames are launch- and tail-bound and throughput rises with the group size even after the group's working set has
+	 * left the 126 MB L2.  With the round-2 kernels: 8.42 us/frame at groups of 64 frames (80 Mpx), 8.20 at 96, 8.10 at 128, 8.00 at
+	 * 256 -- every launch ends in a tail of partly filled SMs and has a ramp at its start, and a group twice as large has half as
+	 * many of them per frame.  128 frames (160 Mpx) it is: the scratch of a lane grows with the group.  Three lanes (streams) with
+	 * one group each in flight cover the launch gaps and tails of one group with the other groups' kernels. */
+	size_t g = (size_t)160 * 1024 * 1024 / nf;
 	if (g < 1) g = 1;
-	if (g > 64) g = 64;
+	if (g > 128) g = 128;
 	const size_t per_lane = ((size_t)n_frames + lanes - 1) / lanes;
 	if (g > per_lane) g = per_lane;
 	/* whole chunks of the hoisted reprojection (16 frames per CTA, 4 per shared-memory word): a group of 33 frames would
