@@ -689,7 +689,8 @@ constexpr size_t HOIST4_SMEM = HOIST4_TBUF * (size_t)HT * 4 + HOIST4_STAGES * 4 
  * 1 (default): the byte is used as the fp32 DENORMAL b * 2^-149 (one PRMT against zero) and the weight carries a factor 2^100
  *    (folded into the x-axis values once per tile): mul.rn(w * 2^100, b * 2^-149) = RN(w * b) * 2^-49 exactly -- scaling by a
  *    power of two commutes with the rounding as long as nothing leaves the normal range, and the smallest non-zero product is
- *    2^-48 * 2^-49.  Every sum and the final 2^23 * 2^-49 rounding add carry the same factor, so the mantissa bits -- the rounded
+ *    2^-50 * 2^-49 (an axis weight is a - floor(a) or its complement for a coordinate a = u - 0.5 with u >= 0.25 or the
+ *    difference rounded away: a multiple of 2^-25 or zero).  Every sum and the final 2^23 * 2^-49 rounding add carry the same factor, so the mantissa bits -- the rounded
  *    integer -- are those of the canonical arithmetic, under another exponent: the "bias" of the integer tail is 0x32800000
  *    instead of 0x4B000000.  Blackwell multiplies denormal operands at full rate (tools/ubench/pipes.cu).  Against variant 0
  *    this removes one FMUL per tap and quad of frames (w * -2^23) and turns the products from 3-operand FFMA2 into FMUL2.
