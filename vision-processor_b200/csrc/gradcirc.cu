@@ -84,13 +84,13 @@ int launch_grad_circ(cudaStream_t stream, int r, const uint32_t* flat, float* gr
 #define VP_GC_LAUNCH(RR)                                                                                                       \
 	case RR: {                                                                                                                 \
 		const int strips = (w + gc_strip_width(RR) - 1) / gc_strip_width(RR);                                                  \
-		const dim3 grid((strips + GC_WARPS - 1) / GC_WARPS, n_seg, n_frames);                                                  \
+		const dim3 grid(((n_frames > 1 ? 2 : 1) * strips + GC_WARPS - 1) / GC_WARPS, n_seg, (n_frames + 1) / 2); /* a pair of frames per blockIdx.z */ \
 		if (o & 1)                                                                                                             \
 			k_grad_circ<RR, true><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(tmap, flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius, \
-			                                                                         need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips); \
+			                                                                         need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips, n_frames); \
 		else                                                                                                                   \
 			k_grad_circ<RR, false><<<grid, GC_WARPS * 32, gc_smem_bytes(RR), stream>>>(tmap, flat, grad, circ, w, h, o, seg_rows, thr, min_score, blob_radius, \
-			                                                                          need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips); \
+			                                                                          need_score, counter, rowcount, masks, wpr, segsum, segmax, striptot, strips, n_frames); \
 	} break;
 	switch (r) {
 		VP_GC_ALL(VP_GC_LAUNCH)

@@ -189,7 +189,7 @@ template <int R, bool O_ODD>
 __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
     k_grad_circ(const __grid_constant__ CUtensorMap tmap, const uint32_t* __restrict__ flat, float* __restrict__ grad, float* __restrict__ circ_out, int w, int h,
                 int o, int seg_rows, float thr, float min_score, int radius, int need_score, int32_t* __restrict__ counter, int32_t* __restrict__ rowcount,
-                uint32_t* __restrict__ masks, int wpr, float* __restrict__ segsum, float* __restrict__ segmax, int32_t* __restrict__ striptot, int n_strips)
+                uint32_t* __restrict__ masks, int wpr, float* __restrict__ segsum, float* __restrict__ segmax, int32_t* __restrict__ striptot, int n_strips, int n_frames)
 {
 	constexpr int K = R - 1, D = R + 2;
 	constexpr int HL = gc_halo_left(R), SW = gc_strip_width(R);
@@ -207,11 +207,15 @@ __global__ void __launch_bounds__(GC_WARPS * 32, R <= 8 ? 4 : 3)
 	}
 	__syncwarp();
 
-	const int strip = blockIdx.x * GC_WARPS + warp;
-	const int f = blockIdx.z;
-	const int xs = strip * SW;
-	if (xs >= w)
+	/* blockIdx.x runs over the strips of a PAIR of frames: 26 strips of a 1224-wide image leave two of a frame's 28 warp slots
+	 * idle for the lifetime of their CTA, the 52 strips of two frames fill 13 CTAs exactly (the warps of a CTA share nothing) */
+	const int task = blockIdx.x * GC_WARPS + warp;
+	const int second = task >= n_strips ? 1 : 0;
+	const int strip = task - (second ? n_strips : 0);
+	const int f = 2 * blockIdx.z + second;
+	if (strip >= n_strips || f >= n_frames)
 		return;
+	const int xs = strip * SW;
 	const int xl = xs - HL - GC_OH;           /* image column of staged word 0 */
 	const int c0 = xs - HL + 2 * lane;        /* this lane's columns: c0 and c0 + 1 (either both inside the image or both outside: w is even) */
 	const int ys = blockIdx.y * seg_rows, ye = min(ys + seg_rows, h);

@@ -643,11 +643,14 @@ int choose_group(vp_ctx* ctx, size_t nf, int n_frames, int lanes)
 	size_t g = (size_t)160 * 1024 * 1024 / nf;
 	if (g < 1) g = 1;
 	if (g > 128) g = 128;
-	const size_t per_lane = ((size_t)n_frames + lanes - 1) / lanes;
-	if (g > per_lane) g = per_lane;
-	/* whole chunks of the hoisted reprojection (16 frames per CTA, 4 per shared-memory word): a group of 33 frames would
-	 * end in a slice of one frame that pays the full per-tile setup (measured: 5.17 instead of 4.89 us/frame) */
-	if (g >= 16) g -= g % 16;
+	/* as many groups as lanes (or a multiple of it when the cap says so), all of about the same size, whole quads of frames
+	 * (the reprojection packs four frames into a shared-memory word): 64 frames of 4096x3000 on three lanes are groups of
+	 * 24 + 24 + 16, not four groups of 16 of which one lane gets two */
+	size_t n_groups = ((size_t)n_frames + g - 1) / g;
+	if (n_groups < (size_t)lanes) n_groups = lanes;
+	n_groups = (n_groups + lanes - 1) / lanes * lanes;
+	g = ((size_t)n_frames + n_groups - 1) / n_groups;
+	if (g >= 4) g = (g + 3) & ~(size_t)3;
 	return (int)g;
 }
 
@@ -1623,8 +1626,11 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 				/* one CTA keeps a tile's weights in registers for `chunk` frames; enough CTAs to fill the GPU several times */
 				int chunk = ctx->hoist_chunk > 0 ? ctx->hoist_chunk : 32; /* 32 at 64-frame groups: 10.46 against 10.56 us/frame at 16 (profiles/r01_group_sweep.txt) */
 				const long long tiles_per_frame = (long long)cdiv(wf, FT_W) * cdiv(hf, FT_H);
-				if (ctx->hoist_chunk <= 0) /* an explicit vp_ctx_set_hoist_chunk is taken as it is (tests, sweeps) */
+				if (ctx->hoist_chunk <= 0) { /* an explicit vp_ctx_set_hoist_chunk is taken as it is (tests, sweeps) */
 					while (chunk > 1 && tiles_per_frame * cdiv(g, chunk) < 8LL * 2 * ctx->sm_count) chunk >>= 1;
+					/* chunks of about the same size, whole quads: a group of 44 frames is 24 + 20, not 32 + 12 */
+					if (chunk >= 4 && g > chunk) chunk = (cdiv(g, cdiv(g, chunk)) + 3) & ~3;
+				}
 				const dim3 grid(cdiv(wf, FT_W), cdiv(hf, FT_H), cdiv(g, chunk));
 				static const int hoist_quads = getenv("VP_HOIST_QUADS") ? atoi(getenv("VP_HOIST_QUADS")) : 1; /* tuning aid / A-B */
 				plan_out[1] = chunk;
