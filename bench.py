@@ -372,7 +372,7 @@ def main():
             copy_pass()
         t1 = time.perf_counter()
         copy_pass()
-        one = time.perf_counter() - t1
+        one = max_over_ranks(time.perf_counter() - t1)  # the same number of passes on every rank
         passes = max(1, int(np.ceil(args.min_seconds / max(one, 1e-6) / max(args.steps, 1))))
         barrier()
         t0 = time.perf_counter()
