@@ -218,6 +218,21 @@ def test_full_size_distorted_tilted_camera_through_the_four_frame_kernel(ctx, po
     assert st["staged"] >= 0.9 * st["tiles"], st
 
 
+def test_automatic_groups_are_balanced_whole_quads(ctx, port):
+    """13 frames on three streams: the library cuts them into groups of the same size rounded up to whole quads of frames (8 + 5,
+    not 4 + 4 + 4 + 1), each group through the four-frame reprojection; every frame against the oracle."""
+    frames = [common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2, n_robots=3, n_balls=2, seed=70 + s_)[1] for s_ in range(13)]
+    p = common.make_case(wq=320, hq=200, fmt=0, k2=0.1, tilt=0.2)[0]
+    ctx.set_hoist_chunk(8)
+    try:
+        got = common.detect_device(ctx, frames, common.to_vp(p))
+    finally:
+        ctx.set_hoist_chunk(0)
+    assert got["plan"]["group"] == 8 and got["plan"]["reproject"] == 4 and got["plan"]["circ"] == 4, got["plan"]
+    for i, fr in enumerate(frames):
+        common.assert_frame_equal(got, i, port.detect(fr, p))
+
+
 def test_tile_stats_of_the_headline_camera(ctx):
     """The undistorted top-down camera of the benchmark: every tile is staged, with 16-byte vectors (2448 % 16 == 0)."""
     p, _ = full_size_case(2448, 2048, n_frames=1)
