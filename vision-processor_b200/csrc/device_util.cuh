@@ -108,7 +108,7 @@ __device__ __forceinline__ float2 add2_opaque(float2 a, float2 b, unsigned long 
  * it have no common FFMA2, so the product keeps its own rounding -- and the add stays a FADD2 (two 64-bit sources), which the
  * scheduler pairs with the ALU pipe's PRMTs at ~1 instruction per clock where the three-source FFMA2 of add2_opaque reaches
  * 0.67 (tools/ubench/pipes.cu).  ONLY for operands and sums that are zero or normal (flushing then never happens): the
- * reprojection's products are >= 2^-99 or exactly 0, see VP_HOIST4_DENORM. */
+ * reprojection's products are >= 2^-99 or exactly 0, see the notes at k_reproject_hoist4. */
 __device__ __forceinline__ float2 add2_ftz(float2 a, float2 b)
 {
 	unsigned long long r;

@@ -651,70 +651,38 @@ __global__ void __launch_bounds__(1024 / PX, 2) k_reproject_hoist(const uint8_t*
  *
  * k_reproject_hoist is bounded by the shared-memory pipe: 16 fp32 tap loads per pixel and frame.  The weights and the tap
  * addresses are the same for every frame of the camera, so the staged planes here hold, per texel, the BYTES OF FOUR
- * FRAMES in one 32-bit word: one LDS fetches a tap for four frames, two PRMT turn a byte pair into the biased floats
- * 2^23 + b, and one FFMA2 with broadcast operands forms the two products (frame A, frame B) x the scalar weight.  Per pixel and frame: 4 LDS instead of 16, the staging does no arithmetic at all (a byte transpose
- * of the four frames' raw vectors: 2 PRMT per staged word) and stores a quarter of the bytes.  The arithmetic per frame is
- * unchanged -- same operations in the same order on the same values: bit-identical to k_reproject_hoist.
+ * FRAMES in one 32-bit word: one LDS fetches a tap for four frames, one PRMT per frame turns its byte into a float and one
+ * FMUL2 with a broadcast operand forms the products (frame A, frame B) x the scalar weight.  Per pixel and frame: 4 LDS instead
+ * of 16; the staging does no arithmetic at all (a byte transpose of the four frames' raw vectors: 2 PRMT per staged word) and
+ * stores a quarter of the bytes.  The arithmetic per frame is the canonical one -- same operations in the same order, every one
+ * rounded on its own -- under a power-of-two scaling (below): bit-identical to k_reproject_hoist and to the oracle.
  *
- * Pipeline per quad of frames: convert(q) -> T | copy(q+1) issued (cp.async, own vectors, lands under the blend) | barrier | blend(q) | barrier.
+ * Pipeline per quad of frames: convert(q) -> T | copy(q+1) issued (cp.async, own vectors, lands under the blend) | barrier |
+ * blend(q) | barrier.  ONE plane buffer, ONE raw stage, the eight axis values of a pixel in registers (the sixteen weights are
+ * formed in the blend), two CTAs per SM: each of the alternatives -- a second plane buffer (one barrier per quad), a second raw
+ * stage, the sixteen weights in registers, a third CTA per SM at 80 registers -- measured 2..15 % slower
+ * (profiles/r01_hoist_sweeps.txt, profiles/r02_sweeps.txt).
+ *
+ * How a staged byte becomes a product: the byte is used as the fp32 DENORMAL b * 2^-149 (one PRMT against zero) and the weight
+ * carries a factor 2^100 (folded into the x-axis values once per tile): mul.rn(w * 2^100, b * 2^-149) = RN(w * b) * 2^-49 exactly --
+ * scaling by a power of two commutes with the rounding as long as nothing leaves the normal range, and the smallest non-zero
+ * product is 2^-50 * 2^-49 (an axis weight is a - floor(a) or its complement for a coordinate a = u - 0.5 with u >= 0.25 or the
+ * difference rounded away: a multiple of 2^-25 or zero).  Every sum and the final 2^23 * 2^-49 rounding add carry the same
+ * factor, so the mantissa bits -- the rounded integer -- are those of the canonical arithmetic under another exponent: the
+ * "bias" of the integer tail is 0x32800000 instead of 0x4B000000.  Blackwell multiplies denormal operands at full rate
+ * (tools/ubench/pipes.cu).  Against fma(2^23 + b, w, -w * 2^23) (round 1) this removes one FMUL per tap and quad of frames and
+ * turns the products from three-source FFMA2 into FMUL2; the sums are FADD2.FTZ (add2_ftz), which ptxas cannot contract.
  * ---------------------------------------------------------------------------------------------- */
-/* build-time A/B (profiles/r01_hoist_sweeps.txt): stages of the raw ring -- 1 (default): a thread refills its ring slots right
- * after converting them, the copy of quad q+1 flies under blend(q); 2: the copy is issued one step earlier, for 31 KB more
- * shared memory per CTA (measured 2 % slower) -- and CTAs per SM the register allocation is sized for (3 = 80 registers
- * with 55 values spilled: measured 15 % slower than 2) */
-#ifndef VP_HOIST4_STAGES
-#define VP_HOIST4_STAGES 1
-#endif
-#ifndef VP_HOIST4_CTAS
-#define VP_HOIST4_CTAS 2
-#endif
-/* build-time A/B: keep the eight axis values of a pixel in registers and form the sixteen weights in the blend (default:
- * 32 instead of 64 registers of frame-invariant state and 16 more FMUL per pixel and quad of frames; the registers it frees
- * go to instruction-level parallelism -- the kernel waits on dependent chains at 4 warps per scheduler -- measured 3 % faster;
- * a third CTA per SM on top of it, 80 registers with 68 B spilled, measured slower again) */
-#ifndef VP_HOIST4_AXES
-#define VP_HOIST4_AXES 1
-#endif
-/* build-time A/B: plane buffers.  2: quad q+1 is converted into the other buffer while slower warps still blend quad q,
- * ONE barrier per quad instead of two -- measured 3 % slower than 1 (32 KB more shared memory per CTA, i.e. less L1 for
- * the coordinate table and the raw vectors; the barrier wait it removes was not the limiter) */
-#ifndef VP_HOIST4_TBUF
-#define VP_HOIST4_TBUF 1
-#endif
-constexpr int HOIST4_STAGES = VP_HOIST4_STAGES;
-constexpr int HOIST4_TBUF = VP_HOIST4_TBUF;
-constexpr size_t HOIST4_SMEM = HOIST4_TBUF * (size_t)HT * 4 + HOIST4_STAGES * 4 * (size_t)HRING;
+constexpr size_t HOIST4_SMEM = (size_t)HT * 4 + 4 * (size_t)HRING;
+constexpr float HOIST4_WSCALE = 1.2676506002282294e30f; /* 2^100 */
+constexpr float HOIST4_ROUND = 1.4901161193847656e-08f; /* 2^23 * 2^-49 = 2^-26 */
 
-/* build-time A/B: how a staged byte becomes a product.
- * 1 (default): the byte is used as the fp32 DENORMAL b * 2^-149 (one PRMT against zero) and the weight carries a factor 2^100
- *    (folded into the x-axis values once per tile): mul.rn(w * 2^100, b * 2^-149) = RN(w * b) * 2^-49 exactly -- scaling by a
- *    power of two commutes with the rounding as long as nothing leaves the normal range, and the smallest non-zero product is
- *    2^-50 * 2^-49 (an axis weight is a - floor(a) or its complement for a coordinate a = u - 0.5 with u >= 0.25 or the
- *    difference rounded away: a multiple of 2^-25 or zero).  Every sum and the final 2^23 * 2^-49 rounding add carry the same factor, so the mantissa bits -- the rounded
- *    integer -- are those of the canonical arithmetic, under another exponent: the "bias" of the integer tail is 0x32800000
- *    instead of 0x4B000000.  Blackwell multiplies denormal operands at full rate (tools/ubench/pipes.cu).  Against variant 0
- *    this removes one FMUL per tap and quad of frames (w * -2^23) and turns the products from 3-operand FFMA2 into FMUL2.
- * 0: the byte is OR-ed under the exponent of 2^23 and fma(2^23 + b, w, -w * 2^23) gives the product. */
-#ifndef VP_HOIST4_DENORM
-#define VP_HOIST4_DENORM 1
-#endif
-constexpr float HOIST4_WSCALE = VP_HOIST4_DENORM ? 1.2676506002282294e30f /* 2^100 */ : 1.0f;
-constexpr float HOIST4_ROUND = VP_HOIST4_DENORM ? 1.4901161193847656e-08f /* 2^23 * 2^-49 = 2^-26 */ : 8388608.0f;
-
-/* build-time A/B: the integer tail of resampling.cl:82-91 (green = mean of the two green planes, dRGB = (2x - y - z + 510) >> 2,
- * packed RGBA) for TWO frames at once in the 16-bit halves of a register (default), or frame by frame on the biased words.
- * The rounded sums leave bias + n with n <= 255 in the low mantissa bits, so PRMT packs (n of frame A, n of frame B); all of the
- * tail is integer arithmetic mod 2^32 on A + 2^16 B whose final per-lane values (2x - y - z + 510) * 64 lie in [0, 65280]:
- * whatever an intermediate borrows from or carries into the other lane is returned by the end.  The factor 64 puts the
- * quotient's eight bits (bits 2..9) into byte 1 of each lane, where PRMT picks them up -- no shifts, no masks.
- * 17 instructions per frame pair against 14 per frame. */
-#ifndef VP_HOIST4_PAIRTAIL
-#define VP_HOIST4_PAIRTAIL 1
-#endif
-/* build-time A/B: the three sums of a channel as FADD2.FTZ (1, see add2_ftz) or as FFMA2 with an opaque 1.0 (0) */
-#ifndef VP_HOIST4_FTZADD
-#define VP_HOIST4_FTZADD 1
-#endif
+/* The integer tail of resampling.cl:82-91 (green = mean of the two green planes, dRGB = (2x - y - z + 510) >> 2, packed RGBA)
+ * for TWO frames at once in the 16-bit halves of a register.  The rounded sums leave bias + n with n <= 255 in the low mantissa
+ * bits, so PRMT packs (n of frame A, n of frame B); all of the tail is integer arithmetic mod 2^32 on A + 2^16 B whose final
+ * per-lane values (2x - y - z + 510) * 64 lie in [0, 65280]: whatever an intermediate borrows from or carries into the other lane
+ * is returned by the end.  The factor 64 puts the quotient's eight bits (bits 2..9) into byte 1 of each lane, where PRMT picks
+ * them up -- no shifts, no masks.  17 instructions per frame pair against 14 per frame on the biased words (drgb_biased). */
 __device__ __forceinline__ void drgb_biased_pair(float2 r, float2 g1, float2 g2, float2 b, uint32_t& px_a, uint32_t& px_b)
 {
 	const uint32_t R = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x5410), B = __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x5410);
@@ -728,74 +696,46 @@ __device__ __forceinline__ void drgb_biased_pair(float2 r, float2 g1, float2 g2,
 	px_b = __byte_perm(rg, ba, 0x7632);
 }
 
-/* w * (byte LO, byte LO+1) of a staged word, two frames at once; bit for bit mul.rn(w, float(b)) (times 2^-49 in variant 1) */
+/* w * 2^100 times (byte LO, byte LO+1) of a staged word as denormals, two frames at once: bit for bit mul.rn(w, float(b)) * 2^-49 */
 template <int LO>
-__device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w, float wm)
+__device__ __forceinline__ float2 weighted_pair(uint32_t wd, float w)
 {
-#if VP_HOIST4_DENORM
-	(void)wm;
 	return mul2(make_float2(__uint_as_float(__byte_perm(wd, 0u, 0x4440 + LO)), __uint_as_float(__byte_perm(wd, 0u, 0x4441 + LO))), make_float2(w, w));
-#else
-	/* fma(2^23 + b, w, -w * 2^23) is the exact product w*b rounded once; wm = -w * 2^23 is exact (a power-of-two scaling) */
-	const float2 b = make_float2(__uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7440 + LO)), __uint_as_float(__byte_perm(wd, 0x4B000000u, 0x7441 + LO)));
-	unsigned long long r;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(b)), "l"(f2_bits(make_float2(w, w))), "l"(f2_bits(make_float2(wm, wm))));
-	return bits_f2(r);
-#endif
 }
 
 template <int FMT, bool FULL>
-__device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][VP_HOIST4_AXES ? 4 : 8], const int (&O)[4][4], uint32_t* __restrict__ out,
-                                             uint32_t nfl, int wf, bool okx, int rows_ok, int n_valid, unsigned long long one2)
+__device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, const float2 (&W)[4][4], const int (&O)[4][4], uint32_t* __restrict__ out,
+                                             uint32_t nfl, int wf, bool okx, int rows_ok, int n_valid)
 {
 	const size_t nfl4 = (size_t)nfl * 4, wf4 = (size_t)wf * 4;
-	(void)nfl4; (void)wf4;
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
 		float2 ab[4], cd[4]; /* channel c: (frame A, frame B) and (frame C, frame D) */
 #pragma unroll
 		for (int c = 0; c < 4; c++) {
 			const uint32_t* t = T + O[k][c];
-			/* weights of channel c: W[k][4*(c>>1) + tap] holds (channel 2*(c>>1), channel 2*(c>>1)+1) */
 #pragma unroll
 			for (int tap = 0; tap < 4; tap++) {
 				const uint32_t wd = t[(tap & 1) + (tap >> 1) * HP];
-#if VP_HOIST4_AXES
-				/* W[k] holds the eight axis values of the pixel (ox, ax, oyp, ayp | oyn, ayn): the weight is formed here, with the
-				 * same single rounding as in the setup of the 64-register variant */
-				const float2 xw = W[k][tap & 1];                                   /* (+0.25 axis, -0.25 axis): ox for tap 0/2, ax for tap 1/3 */
-				const float2 yw = W[k][2 + (tap >> 1)];                            /* (y axis of channels 0/1, y axis of channels 2/3): oy, ay */
+				/* W[k] holds the eight axis values of the pixel (ox, ax | oy, ay, each for the +0.25 and the -0.25 plane): the weight
+				 * is formed here, with the same single rounding as a weight kept in a register */
+				const float2 xw = W[k][tap & 1];        /* (+0.25 axis, -0.25 axis): ox for tap 0/2, ax for tap 1/3 */
+				const float2 yw = W[k][2 + (tap >> 1)]; /* (y axis of channels 0/1, y axis of channels 2/3): oy, ay */
 				float w; /* volatile: the product is frame-invariant and would be hoisted out of the frame loop again (64 registers) */
 				asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(w) : "f"((c & 1) ? xw.y : xw.x), "f"((c >> 1) ? yw.y : yw.x));
-#else
-				const float2 wp = W[k][4 * (c >> 1) + tap];
-				const float w = (c & 1) ? wp.y : wp.x;
-#endif
-#if VP_HOIST4_DENORM
-				const float wm = 0.0f;
-#else
-				const float wm = __fmul_rn(w, -8388608.0f);
-#endif
-				const float2 pab = weighted_pair<0>(wd, w, wm);
-				const float2 pcd = weighted_pair<2>(wd, w, wm);
+				const float2 pab = weighted_pair<0>(wd, w);
+				const float2 pcd = weighted_pair<2>(wd, w);
 				/* ((p00 + p10) + p01) + p11, every sum rounded on its own */
-#if VP_HOIST4_FTZADD
 				ab[c] = tap == 0 ? pab : add2_ftz(pab, ab[c]);
 				cd[c] = tap == 0 ? pcd : add2_ftz(pcd, cd[c]);
-#else
-				ab[c] = tap == 0 ? pab : add2_opaque(pab, ab[c], one2);
-				cd[c] = tap == 0 ? pcd : add2_opaque(pcd, cd[c], one2);
-#endif
 			}
 			ab[c] = add2(ab[c], make_float2(HOIST4_ROUND, HOIST4_ROUND)); /* RNE to integer in the mantissa */
 			cd[c] = add2(cd[c], make_float2(HOIST4_ROUND, HOIST4_ROUND));
 		}
 		const bool in = FULL || (okx && 4 * k < rows_ok);
-#if VP_HOIST4_PAIRTAIL
 		/* the store address walks frame by frame and then to the next row with 64-bit ADDS (IADD3 + IADD3.X: the cheap integer
 		 * path) instead of a scaled 64-bit address per store (LEA + LEA.HI.X on the ALU pipe that the PRMTs saturate) */
 		unsigned char* o = reinterpret_cast<unsigned char*>(out) + (size_t)(4 * k) * wf4;
-		/* the integer tail for two frames at once in 16-bit lanes */
 		constexpr int CR = FMT == FMT_RGGB ? 0 : 1, CG1 = FMT == FMT_RGGB ? 1 : 0, CG2 = FMT == FMT_RGGB ? 2 : 3, CB = FMT == FMT_RGGB ? 3 : 2;
 #pragma unroll
 		for (int j = 0; j < 4; j += 2) {
@@ -811,30 +751,17 @@ __device__ __forceinline__ void hoist4_blend(const uint32_t* __restrict__ T, con
 				*reinterpret_cast<uint32_t*>(o) = pb;
 			o += nfl4;
 		}
-#else
-		uint32_t* o = out + (uint32_t)(4 * k) * (uint32_t)wf;
-#pragma unroll
-		for (int j = 0; j < 4; j++) {
-			uint32_t v[4];
-#pragma unroll
-			for (int c = 0; c < 4; c++)
-				v[c] = __float_as_uint(j == 0 ? ab[c].x : j == 1 ? ab[c].y : j == 2 ? cd[c].x : cd[c].y);
-			const uint32_t px = FMT == FMT_RGGB ? drgb_biased(v[0], (v[1] >> 1) + (v[2] >> 1), v[3]) : drgb_biased(v[1], (v[0] >> 1) + (v[3] >> 1), v[2]);
-			if (in && j < n_valid)
-				o[(size_t)j * nfl] = px;
-		}
-#endif
 	}
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
+__global__ void __launch_bounds__(256, 2) k_reproject_hoist4(const uint8_t* __restrict__ raw0, size_t frame_stride, const float2* __restrict__ lut,
                                                                const TileEntry* __restrict__ table, uint32_t* __restrict__ flat, int wq, int hq,
-                                                               int wf, int hf, int n_frames, int chunk, float one)
+                                                               int wf, int hf, int n_frames, int chunk)
 {
 	extern __shared__ __align__(16) unsigned char hoist_smem[];
 	uint32_t* const T0 = reinterpret_cast<uint32_t*>(hoist_smem);
-	unsigned char* const ring = hoist_smem + HOIST4_TBUF * (size_t)HT * 4;
+	unsigned char* const ring = hoist_smem + (size_t)HT * 4;
 	const int tx = blockIdx.x, ty = blockIdx.y;
 	const int f0 = blockIdx.z * chunk;
 	const int n = min(n_frames, f0 + chunk) - f0;
@@ -902,12 +829,12 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 			s_edge[i] = qx0 < 0 ? 1 : (qx0 != qxc ? 2 : 0);
 		}
 	}
-	unsigned char* const my_ring = ring + tid * 16; /* frame j, vector i of stage st: my_ring + (st*4 + j)*HRING + i*4096 */
+	unsigned char* const my_ring = ring + tid * 16; /* frame j, vector i: my_ring + j*HRING + i*4096 */
 	const int n_quads = (n + 3) >> 2;
 	const uint8_t* next_src = raw; /* first frame of the next quad to copy */
-	auto issue_copy = [&](int q) { /* frames 4q..4q+3 (the last frame repeated past the end) into stage q & 1; always commits */
+	auto issue_copy = [&](int q) { /* frames 4q..4q+3 (the last frame repeated past the end) into the raw stage; always commits */
 		if (vec && q < n_quads) {
-			unsigned char* dst = my_ring + (q % HOIST4_STAGES) * 4 * HRING;
+			unsigned char* dst = my_ring;
 			const int left = n - 4 * q; /* >= 1 */
 			const uint8_t* src = next_src;
 #pragma unroll
@@ -924,7 +851,7 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 		cp_async_commit();
 	};
 	auto convert = [&](int q) { /* this thread's vectors of quad q: byte transpose of the four frames -> T */
-		uint32_t* const T = T0 + (HOIST4_TBUF == 2 ? (q & 1) * HT : 0);
+		uint32_t* const T = T0;
 		if (vec) {
 #pragma unroll
 			for (int i = 0; i < 2; i++) {
@@ -933,7 +860,7 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 				uint32_t fr[4][4];
 #pragma unroll
 				for (int j = 0; j < 4; j++) {
-					uint4 qq = *reinterpret_cast<const uint4*>(my_ring + ((q % HOIST4_STAGES) * 4 + j) * HRING + i * 4096);
+					uint4 qq = *reinterpret_cast<const uint4*>(my_ring + j * HRING + i * 4096);
 					if (s_edge[i]) { /* replicate the edge quad's two bytes over the whole vector */
 						const uint32_t eq = s_edge[i] == 1 ? (qq.x & 0xFFFFu) : (qq.w >> 16);
 						qq.x = qq.y = qq.z = qq.w = eq * 0x00010001u;
@@ -975,7 +902,7 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 	issue_copy(0);
 
 	/* ---- frame-invariant part: weights and tap offsets of this thread's four pixels (the first copy is in flight) ---- */
-	float2 W[4][VP_HOIST4_AXES ? 4 : 8];
+	float2 W[4][4];
 	int O[4][4];
 	const int xmagic = 0x4B400000 + e.ib, ymagic = 0x4B400000 + e.jb;
 #pragma unroll
@@ -986,18 +913,10 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 		float2 ax, ox, ay, oy; /* .x = the +0.25 axis, .y = the -0.25 axis */
 		axis_staged2(add2(make_float2(pos[k].x, pos[k].x), make_float2(0.25f, -0.25f)), xmagic, ixp, ixn, ax, ox);
 		axis_staged2(add2(make_float2(pos[k].y, pos[k].y), make_float2(0.25f, -0.25f)), ymagic, iyp, iyn, ay, oy);
-		const float2 ayp = make_float2(ay.x, ay.x), oyp = make_float2(oy.x, oy.x);
-		const float2 ayn = make_float2(ay.y, ay.y), oyn = make_float2(oy.y, oy.y);
-		/* variant VP_HOIST4_DENORM: the factor 2^100 of the weights rides on the x-axis values (exact: a power of two) */
+		/* the factor 2^100 of the weights rides on the x-axis values (exact: a power of two) */
 		ox = mul2(ox, make_float2(HOIST4_WSCALE, HOIST4_WSCALE));
 		ax = mul2(ax, make_float2(HOIST4_WSCALE, HOIST4_WSCALE));
-#if VP_HOIST4_AXES
-		W[k][0] = ox; W[k][1] = ax; W[k][2] = oy; W[k][3] = ay; /* oy = (oyp, oyn), ay = (ayp, ayn) */
-		(void)oyp; (void)ayp; (void)oyn; (void)ayn;
-#else
-		W[k][0] = mul2(ox, oyp); W[k][1] = mul2(ax, oyp); W[k][2] = mul2(ox, ayp); W[k][3] = mul2(ax, ayp);
-		W[k][4] = mul2(ox, oyn); W[k][5] = mul2(ax, oyn); W[k][6] = mul2(ox, ayn); W[k][7] = mul2(ax, ayn);
-#endif
+		W[k][0] = ox; W[k][1] = ax; W[k][2] = oy; W[k][3] = ay; /* oy = (+y plane, -y plane), ay likewise */
 		O[k][0] = ok ? iyp * HP + ixp : 0; /* pixels outside the image read texel 0 and are not stored */
 		O[k][1] = ok ? HPLANE + iyp * HP + ixn : 0;
 		O[k][2] = ok ? 2 * HPLANE + iyn * HP + ixp : 0;
@@ -1007,31 +926,19 @@ __global__ void __launch_bounds__(256, VP_HOIST4_CTAS) k_reproject_hoist4(const 
 	const int rows_ok = hf - (ty * FT_H + ly);
 	const bool full = (tx + 1) * FT_W <= wf && (ty + 1) * FT_H <= hf;
 	uint32_t* out = flat + (size_t)f0 * nfl + ((uint32_t)(ty * FT_H + ly) * (uint32_t)wf + (uint32_t)gx);
-	const unsigned long long one2 = f2_bits(make_float2(one, one));
-
 #pragma unroll 1
 	for (int q = 0; q < n_quads; q++) {
-		if (HOIST4_STAGES == 2) {
-			issue_copy(q + 1);
-			cp_async_wait<1>(); /* quad q has landed (this thread's vectors) */
-			convert(q);
-		} else { /* one stage: a thread refills its own ring slots as soon as it has converted them */
-			cp_async_wait<0>();
-			convert(q);
-			issue_copy(q + 1);
-		}
+		cp_async_wait<0>(); /* quad q has landed (this thread's vectors) */
+		convert(q);
+		issue_copy(q + 1); /* a thread refills its own ring slots as soon as it has converted them: the copy flies under the blend */
 		__syncthreads();
-		const uint32_t* const T = T0 + (HOIST4_TBUF == 2 ? (q & 1) * HT : 0);
 		const int n_valid = min(4, n - 4 * q);
 		if (full)
-			hoist4_blend<FMT, true>(T, W, O, out, nfl, wf, true, 16, n_valid, one2);
+			hoist4_blend<FMT, true>(T0, W, O, out, nfl, wf, true, 16, n_valid);
 		else
-			hoist4_blend<FMT, false>(T, W, O, out, nfl, wf, okx, rows_ok, n_valid, one2);
+			hoist4_blend<FMT, false>(T0, W, O, out, nfl, wf, okx, rows_ok, n_valid);
 		out += (size_t)4 * nfl;
-		if (HOIST4_TBUF == 1)
-			__syncthreads(); /* everybody has read T before the next quad is converted into it */
-		/* two buffers: quad q+1 goes into the other one, which was last read by blend(q-1) -- and every warp had left that
-		 * before it passed this iteration's barrier */
+		__syncthreads(); /* everybody has read the planes before the next quad is converted into them */
 	}
 }
 

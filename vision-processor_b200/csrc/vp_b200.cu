@@ -1642,9 +1642,9 @@ static int detect_batch_impl(vp_ctx* ctx, const uint8_t* d_raw, int n_frames, co
 						ctx->hoist4_attr = true;
 					}
 					if (p->fmt == VP_FMT_RGGB8)
-						k_reproject_hoist4<FMT_RGGB><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+						k_reproject_hoist4<FMT_RGGB><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk);
 					else
-						k_reproject_hoist4<FMT_GRBG><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk, ctx->one);
+						k_reproject_hoist4<FMT_GRBG><<<grid, 256, HOIST4_SMEM, s>>>(raw, raw_bytes, lut, tiles, flat, p->wq, p->hq, wf, hf, g, chunk);
 				} else {
 					if ((rc = ensure_hoist_attr(ctx))) return rc;
 					if (p->fmt == VP_FMT_RGGB8)
