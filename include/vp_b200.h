@@ -311,8 +311,8 @@ VP_API int vp_copy_to_device(vp_ctx* ctx, void* dev, const void* host, size_t by
 VP_API int vp_host_alloc(size_t bytes, void** out);
 VP_API int vp_host_free(void* p);
 
-/* tuning knob: frames per kernel launch group of the fused path (0 = automatic: about 80 Mpx per launch, in whole
- * 16-frame chunks of the reprojection, at most 64 frames and at most the batch's share of one lane) */
+/* tuning knob: frames per kernel launch group of the fused path (0 = automatic: at most 160 Mpx and 128 frames per launch, as
+ * many groups as lanes -- or a multiple of it -- all of about the same size, whole quads of frames) */
 VP_API int vp_ctx_set_group(vp_ctx* ctx, int frames_per_group);
 /* tuning knob: number of CUDA streams the frame groups of one batch are spread over (1..4, default 3) so that the
  * issue-bound reprojection of one group overlaps the bandwidth-bound scans of another */
